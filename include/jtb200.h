@@ -1,0 +1,87 @@
+/* libjtb200 -- C ABI of the B200-native JTransforms transform path.
+ *
+ * JTransforms (wendykierp/JTransforms) has no FFI of its own: the boundary of the hot path is its public
+ * Java API.  Each entry point below is what a Java shim (Panama FFM downcall or JNI) binds so that the
+ * org.jtransforms classes keep their signatures while the arithmetic runs on the GPU.  Citations are
+ * relative to src/main/java/org/jtransforms in the reference repository.
+ *
+ *   jtb_plan_create   <- constructors DoubleFFT_1D(long) fft/DoubleFFT_1D.java:117-188, DoubleFFT_2D(long,long)
+ *                        fft/DoubleFFT_2D.java:75-98, DoubleFFT_3D(long,long,long) fft/DoubleFFT_3D.java:88-124,
+ *                        DoubleDCT_1D dct/DoubleDCT_1D.java:88-138, DoubleDST_1D dst/DoubleDST_1D.java:59-65,
+ *                        DoubleDHT_1D dht/DoubleDHT_1D.java:60-66 (+ 2-D/3-D and Float twins)
+ *   jtb_exec          <- complexForward fft/DoubleFFT_1D.java:243-263, complexInverse :362-385, realForward
+ *                        :524-561, realForwardFull :678-755, realInverse :946-989, realInverseFull :1112-1195;
+ *                        2-D fft/DoubleFFT_2D.java:115,456,820,956,1077,1212; 3-D fft/DoubleFFT_3D.java:145,
+ *                        :744,:1339,:1480,:1629,:1770; forward/inverse of dct/DoubleDCT_{1,2,3}D.java,
+ *                        dst/DoubleDST_{1,2,3}D.java, dht/DoubleDHT_{1,2,3}D.java
+ *   jtb_exec_batch    <- the caller loop over `offa` the reference needs for batches (no batched API there)
+ *   jtb_exec_device   <- same transforms on device-resident data (benchmarks, multi-GPU composition)
+ *   jtb_lines_c2c_device <- the strided line loops of the N-D drivers (fft/DoubleFFT_3D.java:5505-5713,
+ *                        :6318-6520) exposed so a host layer can run slab-decomposed passes per GPU
+ *
+ * All transforms are in place on interleaved (re, im) or real arrays exactly as the reference lays them out.
+ * Functions return 0 on success or a JTB_ERR_* code; jtb_last_error() returns the thread-local message.
+ * There is no CPU fallback: every compute entry point fails with JTB_ERR_CUDA when no device is present.
+ */
+#ifndef JTB200_H
+#define JTB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jtb_plan jtb_plan;
+
+enum { JTB_OK = 0, JTB_ERR_ARG = 1, JTB_ERR_UNSUPPORTED = 2, JTB_ERR_CUDA = 3, JTB_ERR_OOM = 4, JTB_ERR_NCCL = 5 };
+enum { JTB_FFT = 0, JTB_DCT = 1, JTB_DST = 2, JTB_DHT = 3 };
+enum { JTB_F64 = 0, JTB_F32 = 1 };
+enum {
+  JTB_C2C_FORWARD = 0, /* complexForward */
+  JTB_C2C_INVERSE = 1, /* complexInverse(scale) */
+  JTB_R2C_PACKED = 2,  /* realForward (packed half spectrum) */
+  JTB_R2C_FULL = 3,    /* realForwardFull */
+  JTB_C2R_PACKED = 4,  /* realInverse(scale) */
+  JTB_C2R_FULL = 5,    /* realInverseFull(scale) */
+  JTB_R2R_FORWARD = 6, /* DCT/DST/DHT forward(scale) */
+  JTB_R2R_INVERSE = 7  /* DCT/DST/DHT inverse(scale) */
+};
+
+/* rank 1..3, dims[0..rank) = (n) | (rows, columns) | (slices, rows, columns); device = CUDA ordinal */
+int jtb_plan_create(jtb_plan** out, int kind, int prec, int rank, const int64_t* dims, int device);
+int jtb_plan_destroy(jtb_plan* plan);
+/* number of array elements (doubles/floats) the op reads+writes for one transform */
+int64_t jtb_plan_elements(const jtb_plan* plan, int op);
+
+/* host array in, host array out (same addresses): H2D, kernels, D2H, synchronised on return */
+int jtb_exec(jtb_plan* plan, int op, void* host_a, int64_t offa, int scale);
+/* `howmany` transforms, transform b starting at host_a[offa + b*dist] */
+int jtb_exec_batch(jtb_plan* plan, int op, void* host_a, int64_t offa, int64_t howmany, int64_t dist, int scale);
+/* device-resident: dev_a is a device pointer (16-byte aligned); asynchronous on `stream` (cudaStream_t, may be 0) */
+int jtb_exec_device(jtb_plan* plan, int op, void* dev_a, int64_t howmany, int64_t dist, int scale, void* stream);
+
+/* in-place complex FFT of length n along `nlines` strided lines of a device array (units: complex elements):
+ * line l = i0 + c0*i3 starts at i0*d0 + i3*d3, its element j at + j*stride.  scale multiplies the output. */
+int jtb_lines_c2c_device(int prec, int device, void* dev_a, int64_t n, int64_t nlines, int64_t c0, int64_t d0,
+                         int64_t d3, int64_t stride, int inverse, double scale, void* stream);
+
+/* pinned host memory for callers that want DMA-speed jtb_exec (Java: off-heap segments / LargeArray storage) */
+int jtb_host_alloc(void** out, int64_t bytes);
+int jtb_host_free(void* p);
+
+/* synthetic input: a[i] = lo + (hi-lo) * u(seed + i), counter-based (bench and parity harness) */
+int jtb_fill_uniform_device(int prec, int device, void* dev_a, int64_t count, uint64_t seed, double lo, double hi,
+                            void* stream);
+
+/* test knob: cap the single-pass line length (log2) so small sizes exercise the two-pass path; 0 = default */
+int jtb_debug_set_limits(int logn_contig, int logn_strided);
+
+int jtb_device_count(void);
+int64_t jtb_launch_count(int device); /* kernels launched so far on that device's context */
+const char* jtb_last_error(void);
+const char* jtb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,81 @@
+"""ctypes binding of libjtb200.so (the C ABI declared in include/jtb200.h).
+
+There is no CPU fallback: if the CUDA library is missing or no device is present, every transform
+raises.  ``use(path)`` exists so the CPU-only test-suite can point the host layer at the
+g++-emulated build of the very same sources (tests/emu); the product never does that.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(HERE, "libjtb200.so")
+
+OK, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_OOM, ERR_NCCL = range(6)
+FFT, DCT, DST, DHT = range(4)
+F64, F32 = 0, 1
+(C2C_FORWARD, C2C_INVERSE, R2C_PACKED, R2C_FULL, C2R_PACKED, C2R_FULL, R2R_FORWARD, R2R_INVERSE) = range(8)
+
+SYMBOLS = [
+    "jtb_plan_create", "jtb_plan_destroy", "jtb_plan_elements", "jtb_exec", "jtb_exec_batch", "jtb_exec_device",
+    "jtb_lines_c2c_device", "jtb_host_alloc", "jtb_host_free", "jtb_fill_uniform_device", "jtb_device_count",
+    "jtb_launch_count", "jtb_last_error", "jtb_version", "jtb_debug_set_limits",
+]
+
+_lib = None
+
+
+class JtbError(RuntimeError):
+    """CUDA / resource failure inside libjtb200 (Java shim: IllegalStateException)."""
+
+
+def _bind(lib):
+    i64, vp, ci = C.c_int64, C.c_void_p, C.c_int
+    lib.jtb_plan_create.argtypes = [C.POINTER(vp), ci, ci, ci, C.POINTER(i64), ci]
+    lib.jtb_plan_destroy.argtypes = [vp]
+    lib.jtb_plan_elements.argtypes = [vp, ci]
+    lib.jtb_plan_elements.restype = i64
+    lib.jtb_exec.argtypes = [vp, ci, vp, i64, ci]
+    lib.jtb_exec_batch.argtypes = [vp, ci, vp, i64, i64, i64, ci]
+    lib.jtb_exec_device.argtypes = [vp, ci, vp, i64, i64, ci, vp]
+    lib.jtb_lines_c2c_device.argtypes = [ci, ci, vp, i64, i64, i64, i64, i64, i64, ci, C.c_double, vp]
+    lib.jtb_host_alloc.argtypes = [C.POINTER(vp), i64]
+    lib.jtb_host_free.argtypes = [vp]
+    lib.jtb_fill_uniform_device.argtypes = [ci, ci, vp, i64, C.c_uint64, C.c_double, C.c_double, vp]
+    lib.jtb_device_count.restype = ci
+    lib.jtb_debug_set_limits.argtypes = [ci, ci]
+    lib.jtb_launch_count.argtypes = [ci]
+    lib.jtb_launch_count.restype = i64
+    lib.jtb_last_error.restype = C.c_char_p
+    lib.jtb_version.restype = C.c_char_p
+    return lib
+
+
+def use(path: str):
+    """Load the C-ABI library from an explicit path (test hook)."""
+    global _lib
+    _lib = _bind(C.CDLL(path))
+    return _lib
+
+
+def get():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(DEFAULT_LIB):
+            raise JtbError(
+                "libjtb200.so is not built (%s). Run `python -m jtransforms_b200.build`; "
+                "jtransforms_b200 has no CPU fallback." % DEFAULT_LIB)
+        use(DEFAULT_LIB)
+    return _lib
+
+
+def check(status: int):
+    if status == OK:
+        return
+    msg = get().jtb_last_error().decode("utf-8", "replace")
+    if status == ERR_ARG:
+        raise ValueError(msg)            # Java shim: IllegalArgumentException(msg)
+    if status == ERR_OOM:
+        raise MemoryError(msg)
+    raise JtbError("libjtb200 error %d: %s" % (status, msg))

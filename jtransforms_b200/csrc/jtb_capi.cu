@@ -1,0 +1,335 @@
+// C ABI of libjtb200 (include/jtb200.h): plans, the N-D drivers that sequence the line kernels, and
+// the host-pointer / device-pointer execution entry points.
+//
+// N-D drivers replace the reference's row/column/slice loops over the ConcurrencyUtils thread pool:
+//   2-D complex  fft/DoubleFFT_2D.java:115-213 (+ cdft2d_subth :3352-3529)
+//   2-D real     fft/DoubleFFT_2D.java:820-838 (xdft2d0_subth1 :3100, cdft2d_subth :3352, rdft2d_sub :2544)
+//   3-D complex  fft/DoubleFFT_3D.java:145-325 (xdft3da_subth2 :5505, cdft3db_subth :6318)
+//   3-D real     fft/DoubleFFT_3D.java:1339-1355 (rdft3d_sub :6909-7021)
+//   DCT/DST/DHT  dct/DoubleDCT_2D.java:104-183, dht/DoubleDHT_2D.java:102-190 (+ yTransform :1288-1309)
+#include <cstring>
+
+#include "../../include/jtb200.h"
+#include "jtb_engine.h"
+
+using namespace jtb;
+
+struct jtb_plan {
+  int kind, prec, rank, device;
+  i64 dims[3];
+  i64 total;
+  Ctx* ctx;
+};
+
+namespace {
+
+template <typename T> int nd_c2c(Engine<T>& e, cx<T>* a, int rank, const i64* d, bool inverse, bool scale) {
+  typedef cx<T> C;
+  (void)sizeof(C);
+  if (rank == 1) return e.c2c_lines(a, geo_contig(d[0]), 1, d[0], inverse, scale, (T)(1.0 / (double)d[0]));
+  if (rank == 2) {
+    const i64 R = d[0], Cn = d[1];
+    JTB_TRY(e.c2c_lines(a, geo_contig(Cn), R, Cn, inverse, false, (T)1));
+    return e.c2c_lines(a, geo_make(Cn, 1, R * Cn, Cn), Cn, R, inverse, scale, (T)(1.0 / ((double)R * (double)Cn)));
+  }
+  const i64 S = d[0], R = d[1], Cn = d[2];
+  JTB_TRY(e.c2c_lines(a, geo_contig(Cn), S * R, Cn, inverse, false, (T)1));
+  JTB_TRY(e.c2c_lines(a, geo_make(Cn, 1, R * Cn, Cn), Cn * S, R, inverse, false, (T)1));
+  return e.c2c_lines(a, geo_make(R * Cn, 1, S * R * Cn, R * Cn), R * Cn, S, inverse, scale,
+                     (T)(1.0 / ((double)S * (double)R * (double)Cn)));
+}
+
+template <typename T> int untangle(Engine<T>& e, T* a, int rank, const i64* d, int dir) {
+  unsigned g, b;
+  if (rank == 2) {
+    if (d[0] / 2 - 1 < 1) return ST_OK;
+    grid_for(d[0] / 2 - 1, &g, &b);
+    JTB_LAUNCH(k_untangle2d<T>, g, b, 0, e.st, a, d[0], d[1], dir);
+  } else {
+    grid_for(d[0] * (d[1] / 2 + 1), &g, &b);
+    JTB_LAUNCH(k_untangle3d<T>, g, b, 0, e.st, a, d[0], d[1], d[2], dir);
+  }
+  JTB_CUDA(cudaGetLastError());
+  e.ctx->launches++;
+  return ST_OK;
+}
+
+template <typename T> int real_packed(Engine<T>& e, T* a, int rank, const i64* d, bool inverse, bool scale) {
+  typedef cx<T> C;
+  if (rank == 1) {
+    return inverse ? e.real_inverse_lines(a, geo_contig(d[0]), 1, d[0], scale)
+                   : e.real_forward_lines(a, geo_contig(d[0]), 1, d[0]);
+  }
+  for (int k = 0; k < rank; ++k)
+    if (!is_pow2(d[k])) {
+      set_error(rank == 2 ? "rows and columns must be power of two numbers"
+                          : "slices, rows and columns must be power of two numbers");
+      return ST_ARG;
+    }
+  C* ac = (C*)a;
+  if (rank == 2) {
+    const i64 R = d[0], Cn = d[1], H = Cn / 2;
+    if (!inverse) {
+      JTB_TRY(e.real_forward_lines(a, geo_contig(Cn), R, Cn));
+      JTB_TRY(e.c2c_lines(ac, geo_make(H, 1, R * H, H), H, R, false, false, (T)1));
+      return untangle(e, a, 2, d, +1);
+    }
+    JTB_TRY(untangle(e, a, 2, d, -1));
+    JTB_TRY(e.c2c_lines(ac, geo_make(H, 1, R * H, H), H, R, true, scale, (T)(1.0 / (double)R)));
+    return e.real_inverse_lines(a, geo_contig(Cn), R, Cn, scale);
+  }
+  const i64 S = d[0], R = d[1], Cn = d[2], H = Cn / 2;
+  if (!inverse) {
+    JTB_TRY(e.real_forward_lines(a, geo_contig(Cn), S * R, Cn));
+    JTB_TRY(e.c2c_lines(ac, geo_make(H, 1, R * H, H), H * S, R, false, false, (T)1));
+    JTB_TRY(e.c2c_lines(ac, geo_make(R * H, 1, S * R * H, R * H), R * H, S, false, false, (T)1));
+    return untangle(e, a, 3, d, +1);
+  }
+  JTB_TRY(untangle(e, a, 3, d, -1));
+  JTB_TRY(e.c2c_lines(ac, geo_make(R * H, 1, S * R * H, R * H), R * H, S, true, scale, (T)(1.0 / (double)S)));
+  JTB_TRY(e.c2c_lines(ac, geo_make(H, 1, R * H, H), H * S, R, true, scale, (T)(1.0 / (double)R)));
+  return e.real_inverse_lines(a, geo_contig(Cn), S * R, Cn, scale);
+}
+
+// realForwardFull / realInverseFull: total reals in the first half of a 2*total array -> full complex result
+template <typename T> int real_full(Engine<T>& e, T* a, int rank, const i64* d, i64 total, bool inverse, bool scale) {
+  typedef cx<T> C;
+  JTB_TRY(e.ctx->ensure(e.ctx->work[WK_FULL], (size_t)total * sizeof(C)));
+  C* wk = (C*)e.ctx->work[WK_FULL].p;
+  R2RParams<T> p;
+  p.a = a; p.work = wk; p.g = geo_contig(total); p.line_base = 0; p.nlines = 1; p.n = total;
+  p.mode = PRE_R2C; p.dst = 0; p.f0 = p.f = (T)1; p.dtw = nullptr;
+  unsigned g, b;
+  grid_for(total, &g, &b);
+  JTB_LAUNCH(k_r2r_pre<T>, g, b, 0, e.st, p);
+  JTB_CUDA(cudaGetLastError());
+  e.ctx->launches++;
+  JTB_TRY(nd_c2c(e, wk, rank, d, inverse, scale));
+  JTB_CUDA(cudaMemcpyAsync(a, wk, (size_t)total * sizeof(C), cudaMemcpyDeviceToDevice, e.st));
+  return ST_OK;
+}
+
+template <typename T> int nd_r2r(Engine<T>& e, T* a, int kind, int rank, const i64* d, bool inverse, bool scale) {
+  if (rank == 1) return e.r2r_lines(a, geo_contig(d[0]), 1, d[0], kind, inverse, scale);
+  unsigned g, b;
+  if (rank == 2) {
+    const i64 R = d[0], Cn = d[1];
+    JTB_TRY(e.r2r_lines(a, geo_make(Cn, 1, R * Cn, Cn), Cn, R, kind, inverse, scale));
+    JTB_TRY(e.r2r_lines(a, geo_contig(Cn), R, Cn, kind, inverse, scale));
+    if (kind == JTB_DHT) {
+      grid_for((R / 2 + 1) * (Cn / 2 + 1), &g, &b);
+      JTB_LAUNCH(k_ytransform2d<T>, g, b, 0, e.st, a, R, Cn);
+      JTB_CUDA(cudaGetLastError());
+      e.ctx->launches++;
+    }
+    return ST_OK;
+  }
+  const i64 S = d[0], R = d[1], Cn = d[2];
+  JTB_TRY(e.r2r_lines(a, geo_contig(Cn), S * R, Cn, kind, inverse, scale));
+  JTB_TRY(e.r2r_lines(a, geo_make(Cn, 1, R * Cn, Cn), Cn * S, R, kind, inverse, scale));
+  JTB_TRY(e.r2r_lines(a, geo_make(R * Cn, 1, S * R * Cn, R * Cn), R * Cn, S, kind, inverse, scale));
+  if (kind == JTB_DHT) {
+    grid_for((S / 2 + 1) * (R / 2 + 1) * (Cn / 2 + 1), &g, &b);
+    JTB_LAUNCH(k_ytransform3d<T>, g, b, 0, e.st, a, S, R, Cn);
+    JTB_CUDA(cudaGetLastError());
+    e.ctx->launches++;
+  }
+  return ST_OK;
+}
+
+bool op_valid(const jtb_plan* p, int op) {
+  if (p->kind == JTB_FFT) return op >= JTB_C2C_FORWARD && op <= JTB_C2R_FULL;
+  return op == JTB_R2R_FORWARD || op == JTB_R2R_INVERSE;
+}
+
+template <typename T>
+int run_device(jtb_plan* p, int op, T* a, i64 howmany, i64 dist, bool scale, cudaStream_t st) {
+  typedef cx<T> C;
+  Engine<T> e(p->ctx, st);
+  const i64* d = p->dims;
+  if (p->rank == 1 && d[0] == 1) return ST_OK;   // n == 1 is a no-op (fft/DoubleFFT_1D.java:248-250)
+  // batched 1-D fast paths: one launch sequence over all lines
+  if (p->rank == 1 && howmany > 1) {
+    const i64 n = d[0];
+    switch (op) {
+      case JTB_C2C_FORWARD:
+      case JTB_C2C_INVERSE:
+        if (dist % 2) { set_error("dist must be even for complex transforms"); return ST_ARG; }
+        return e.c2c_lines((C*)a, geo_contig(dist / 2), howmany, n, op == JTB_C2C_INVERSE, scale && op == JTB_C2C_INVERSE,
+                           (T)(1.0 / (double)n));
+      case JTB_R2C_PACKED: return e.real_forward_lines(a, geo_contig(dist), howmany, n);
+      case JTB_C2R_PACKED: return e.real_inverse_lines(a, geo_contig(dist), howmany, n, scale);
+      case JTB_R2R_FORWARD:
+      case JTB_R2R_INVERSE: return e.r2r_lines(a, geo_contig(dist), howmany, n, p->kind, op == JTB_R2R_INVERSE, scale);
+      default: break;
+    }
+  }
+  for (i64 b = 0; b < howmany; ++b) {
+    T* ab = a + b * dist;
+    int s = ST_OK;
+    switch (op) {
+      case JTB_C2C_FORWARD: s = nd_c2c(e, (C*)ab, p->rank, d, false, false); break;
+      case JTB_C2C_INVERSE: s = nd_c2c(e, (C*)ab, p->rank, d, true, scale); break;
+      case JTB_R2C_PACKED: s = real_packed(e, ab, p->rank, d, false, false); break;
+      case JTB_C2R_PACKED: s = real_packed(e, ab, p->rank, d, true, scale); break;
+      case JTB_R2C_FULL: s = real_full(e, ab, p->rank, d, p->total, false, false); break;
+      case JTB_C2R_FULL: s = real_full(e, ab, p->rank, d, p->total, true, scale); break;
+      case JTB_R2R_FORWARD: s = nd_r2r(e, ab, p->kind, p->rank, d, false, scale); break;
+      case JTB_R2R_INVERSE: s = nd_r2r(e, ab, p->kind, p->rank, d, true, scale); break;
+      default: set_error("unknown op %d", op); return ST_ARG;
+    }
+    if (s != ST_OK) return s;
+  }
+  return ST_OK;
+}
+
+int check_plan(const jtb_plan* p, int op) {
+  if (!p) { set_error("null plan"); return ST_ARG; }
+  if (!op_valid(p, op)) { set_error("op %d is not valid for this plan kind", op); return ST_ARG; }
+  return ST_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int jtb_plan_create(jtb_plan** out, int kind, int prec, int rank, const int64_t* dims, int device) {
+  if (!out || !dims) { set_error("null argument"); return ST_ARG; }
+  *out = nullptr;
+  if (kind < JTB_FFT || kind > JTB_DHT || (prec != JTB_F64 && prec != JTB_F32) || rank < 1 || rank > 3) {
+    set_error("bad kind/precision/rank");
+    return ST_ARG;
+  }
+  if (rank == 1) {
+    if (dims[0] < 1) { set_error("n must be greater than 0"); return ST_ARG; }
+  } else {
+    for (int k = 0; k < rank; ++k)
+      if (dims[k] <= 1) {
+        set_error(rank == 2 ? "rows and columns must be greater than 1" : "slices, rows and columns must be greater than 1");
+        return ST_ARG;
+      }
+  }
+  Ctx* ctx = get_ctx(device);
+  if (!ctx) return ST_CUDA;
+  jtb_plan* p = new jtb_plan();
+  p->kind = kind; p->prec = prec; p->rank = rank; p->device = device; p->ctx = ctx;
+  p->total = 1;
+  for (int k = 0; k < 3; ++k) { p->dims[k] = k < rank ? dims[k] : 1; p->total *= p->dims[k]; }
+  *out = p;
+  return ST_OK;
+}
+
+int jtb_plan_destroy(jtb_plan* plan) {
+  delete plan;
+  return ST_OK;
+}
+
+int64_t jtb_plan_elements(const jtb_plan* p, int op) {
+  if (!p) return 0;
+  switch (op) {
+    case JTB_C2C_FORWARD: case JTB_C2C_INVERSE: case JTB_R2C_FULL: case JTB_C2R_FULL: return 2 * p->total;
+    default: return p->total;
+  }
+}
+
+int jtb_exec_device(jtb_plan* p, int op, void* dev_a, int64_t howmany, int64_t dist, int scale, void* stream) {
+  JTB_TRY(check_plan(p, op));
+  if (!dev_a) { set_error("null data pointer"); return ST_ARG; }
+  if (howmany < 1) return ST_OK;
+  std::lock_guard<std::mutex> lk(p->ctx->mu);
+  JTB_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  return p->prec == JTB_F64 ? run_device<double>(p, op, (double*)dev_a, howmany, dist, scale != 0, st)
+                            : run_device<float>(p, op, (float*)dev_a, howmany, dist, scale != 0, st);
+}
+
+int jtb_exec_batch(jtb_plan* p, int op, void* host_a, int64_t offa, int64_t howmany, int64_t dist, int scale) {
+  JTB_TRY(check_plan(p, op));
+  if (!host_a) { set_error("null data pointer"); return ST_ARG; }
+  if (howmany < 1) return ST_OK;
+  if (offa < 0) { set_error("negative offset"); return ST_ARG; }
+  const i64 elems = jtb_plan_elements(p, op);
+  if (howmany > 1 && dist < elems) { set_error("dist smaller than one transform"); return ST_ARG; }
+  const size_t esz = p->prec == JTB_F64 ? 8 : 4;
+  const i64 span = (howmany - 1) * dist + elems;
+  const bool full = op == JTB_R2C_FULL || op == JTB_C2R_FULL;
+  const i64 in_span = (full && howmany == 1) ? p->total : span;
+  Ctx* c = p->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  JTB_CUDA(cudaSetDevice(p->device));
+  JTB_TRY(c->ensure(c->io, (size_t)span * esz));
+  char* h = (char*)host_a + (size_t)offa * esz;
+  JTB_CUDA(cudaMemcpyAsync(c->io.p, h, (size_t)in_span * esz, cudaMemcpyHostToDevice, c->stream));
+  int s = p->prec == JTB_F64 ? run_device<double>(p, op, (double*)c->io.p, howmany, dist, scale != 0, c->stream)
+                             : run_device<float>(p, op, (float*)c->io.p, howmany, dist, scale != 0, c->stream);
+  if (s != ST_OK) { cudaStreamSynchronize(c->stream); return s; }
+  JTB_CUDA(cudaMemcpyAsync(h, c->io.p, (size_t)span * esz, cudaMemcpyDeviceToHost, c->stream));
+  JTB_CUDA(cudaStreamSynchronize(c->stream));
+  return ST_OK;
+}
+
+int jtb_exec(jtb_plan* p, int op, void* host_a, int64_t offa, int scale) {
+  return jtb_exec_batch(p, op, host_a, offa, 1, 0, scale);
+}
+
+int jtb_lines_c2c_device(int prec, int device, void* dev_a, int64_t n, int64_t nlines, int64_t c0, int64_t d0,
+                         int64_t d3, int64_t stride, int inverse, double scale, void* stream) {
+  if (!dev_a || n < 1 || nlines < 0 || c0 < 1 || stride < 1) { set_error("bad line geometry"); return ST_ARG; }
+  Ctx* c = get_ctx(device);
+  if (!c) return ST_CUDA;
+  std::lock_guard<std::mutex> lk(c->mu);
+  JTB_CUDA(cudaSetDevice(device));
+  Geo g = geo_make(c0, d0, d3, stride);
+  const bool has_scale = scale != 1.0;
+  if (prec == JTB_F64) {
+    Engine<double> e(c, (cudaStream_t)stream);
+    return e.c2c_lines((double2*)dev_a, g, nlines, n, inverse != 0, has_scale, scale);
+  }
+  Engine<float> e(c, (cudaStream_t)stream);
+  return e.c2c_lines((float2*)dev_a, g, nlines, n, inverse != 0, has_scale, (float)scale);
+}
+
+int jtb_host_alloc(void** out, int64_t bytes) {
+  if (!out || bytes < 0) { set_error("bad argument"); return ST_ARG; }
+  if (!get_ctx(0)) return ST_CUDA;
+  JTB_CUDA(cudaHostAlloc(out, (size_t)(bytes < 16 ? 16 : bytes), cudaHostAllocDefault));
+  return ST_OK;
+}
+int jtb_host_free(void* p) {
+  if (p) JTB_CUDA(cudaFreeHost(p));
+  return ST_OK;
+}
+
+int jtb_fill_uniform_device(int prec, int device, void* dev_a, int64_t count, uint64_t seed, double lo, double hi,
+                            void* stream) {
+  Ctx* c = get_ctx(device);
+  if (!c) return ST_CUDA;
+  if (!dev_a || count < 0) { set_error("bad argument"); return ST_ARG; }
+  JTB_CUDA(cudaSetDevice(device));
+  unsigned g, b;
+  grid_for(count, &g, &b);
+  if (prec == JTB_F64) JTB_LAUNCH(k_fill_uniform<double>, g, b, 0, (cudaStream_t)stream, (double*)dev_a, count, (unsigned long long)seed, lo, hi);
+  else JTB_LAUNCH(k_fill_uniform<float>, g, b, 0, (cudaStream_t)stream, (float*)dev_a, count, (unsigned long long)seed, (float)lo, (float)hi);
+  JTB_CUDA(cudaGetLastError());
+  c->launches++;
+  return ST_OK;
+}
+
+int jtb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+int64_t jtb_launch_count(int device) {
+  Ctx* c = get_ctx(device);
+  return c ? c->launches : -1;
+}
+int jtb_debug_set_limits(int logn_contig, int logn_strided) {
+  g_limit_contig = logn_contig;
+  g_limit_strided = logn_strided;
+  return ST_OK;
+}
+const char* jtb_last_error(void) { return last_error(); }
+const char* jtb_version(void) { return "jtb200 0.1 (sm_100a)"; }
+
+}  // extern "C"

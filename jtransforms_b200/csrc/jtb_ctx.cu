@@ -1,0 +1,94 @@
+// Per-device context of libjtb200: library stream, growable workspaces, device table cache,
+// thread-local error text.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "jtb_engine.h"
+
+namespace jtb {
+
+static thread_local char g_err[512] = "";
+int g_limit_contig = 0, g_limit_strided = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error '%s' in %s", cudaGetErrorString(e), what);
+  return e == cudaErrorMemoryAllocation ? ST_OOM : ST_CUDA;
+}
+
+void grid_for(i64 work_items, unsigned* grid, unsigned* block) {
+  const unsigned b = 256;
+  i64 g = (work_items + b - 1) / b;
+  const i64 cap = 148LL * 8 * 4;     // grid-stride loops: a few waves of 148 SMs x 8 CTAs
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  *grid = (unsigned)g;
+  *block = b;
+}
+
+int Ctx::ensure(DevBuf& b, size_t bytes) {
+  if (b.bytes >= bytes && b.p) return ST_OK;
+  if (b.p) {
+    JTB_CUDA(cudaDeviceSynchronize());   // kernels in flight may still use the old buffer
+    JTB_CUDA(cudaFree(b.p));
+    b.p = nullptr; b.bytes = 0;
+  }
+  size_t want = bytes < 256 ? 256 : bytes;
+  JTB_CUDA(cudaMalloc(&b.p, want));
+  b.bytes = want;
+  return ST_OK;
+}
+
+int Ctx::put_table(const std::string& key, const void* host, size_t bytes, void** dev_out) {
+  void* d = nullptr;
+  JTB_CUDA(cudaMalloc(&d, bytes < 16 ? 16 : bytes));
+  // synchronous copy: the host vector dies when the caller returns
+  JTB_CUDA(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
+  tables[key] = d;
+  *dev_out = d;
+  return ST_OK;
+}
+
+static std::mutex g_ctx_mu;
+static std::map<int, Ctx*> g_ctx;
+
+Ctx* get_ctx(int device) {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  auto it = g_ctx.find(device);
+  if (it != g_ctx.end()) return it->second;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count < 1) {
+    set_error("no CUDA device available (%s): libjtb200 has no CPU fallback", cudaGetErrorString(e));
+    return nullptr;
+  }
+  if (device < 0 || device >= count) { set_error("device %d out of range (have %d)", device, count); return nullptr; }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { cuda_fail(e, "cudaSetDevice"); return nullptr; }
+  Ctx* c = new Ctx();
+  c->device = device;
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    cuda_fail(e, "cudaStreamCreate");
+    delete c;
+    return nullptr;
+  }
+  g_ctx[device] = c;
+  return c;
+}
+
+__global__ void k_cast_c64_c32(const double2* in, float2* out, i64 count) {
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (i64)gridDim.x * blockDim.x) {
+    const double2 z = in[i];
+    float2 r; r.x = (float)z.x; r.y = (float)z.y;
+    out[i] = r;
+  }
+}
+
+}  // namespace jtb

@@ -1,0 +1,105 @@
+// Host-side engine of libjtb200: per-device context (stream, workspaces, twiddle/chirp
+// table caches) and the typed transform drivers that turn one JTransforms API call into
+// a short sequence of sm_100a kernel launches.
+#pragma once
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "jtb_elem.cuh"
+#include "jtb_tile_host.h"
+
+namespace jtb {
+
+enum { ST_OK = 0, ST_ARG = 1, ST_UNSUPPORTED = 2, ST_CUDA = 3, ST_OOM = 4, ST_NCCL = 5 };
+
+void set_error(const char* fmt, ...);
+const char* last_error();
+int cuda_fail(cudaError_t e, const char* what);   // records message, returns ST_CUDA / ST_OOM
+
+#define JTB_CUDA(expr)                                                   \
+  do {                                                                   \
+    cudaError_t _e = (expr);                                             \
+    if (_e != cudaSuccess) return ::jtb::cuda_fail(_e, #expr);           \
+  } while (0)
+#define JTB_TRY(expr)                    \
+  do {                                   \
+    int _s = (expr);                     \
+    if (_s != ::jtb::ST_OK) return _s;   \
+  } while (0)
+
+static inline bool is_pow2(i64 n) { return n > 0 && (n & (n - 1)) == 0; }
+static inline int ilog2(i64 n) { int l = 0; while ((1LL << l) < n) ++l; return l; }
+static inline i64 next_pow2(i64 n) { return 1LL << ilog2(n); }
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+enum { WK_FOURSTEP = 0, WK_BLUE = 1, WK_REAL = 2, WK_FULL = 3, WK_COUNT = 4 };
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;       // library stream for the host-pointer API
+  std::mutex mu;
+  DevBuf work[WK_COUNT];
+  DevBuf io;                           // device copy of the caller's host array
+  std::map<std::string, void*> tables; // device tables keyed by name
+  size_t work_cap = (size_t)8 << 30;   // chunk limit per workspace
+  long launches = 0;                   // kernels launched (bench.py reports this)
+  bool tile_init_done[2] = {false, false};
+  int ensure(DevBuf& b, size_t bytes);
+  void* table(const std::string& key) { auto it = tables.find(key); return it == tables.end() ? nullptr : it->second; }
+  int put_table(const std::string& key, const void* host, size_t bytes, void** dev_out);
+  int adopt_table(const std::string& key, void* dev) { tables[key] = dev; return ST_OK; }
+};
+
+extern int g_limit_contig, g_limit_strided;   // test knobs: force the two-pass path at small sizes (0 = off)
+Ctx* get_ctx(int device);   // creates on first use; nullptr + error on failure
+void grid_for(i64 work_items, unsigned* grid, unsigned* block);
+
+// Fusion options of one power-of-two c2c call (see TileParams)
+template <typename T> struct Fuse {
+  int swap_in = 0, swap_in2 = 0, swap_out1 = 0, swap_out = 0;
+  const cx<T>* premul = nullptr;  int premul_conj = 0;
+  const cx<T>* postmul = nullptr; int postmul_conj = 0;
+  i64 valid_in = -1, valid_out = -1;
+  int has_scale = 0; T scale = 1;
+};
+
+template <typename T> struct Engine {
+  typedef cx<T> C;
+  Ctx* ctx;
+  cudaStream_t st;
+  Engine(Ctx* c, cudaStream_t s) : ctx(c), st(s) {}
+  static const char* pname();
+  static int max_logn_contig();    // longest line one CTA transforms (contiguous lines)
+  static int max_logn_strided();   // ... when several adjacent strided lines must share the CTA
+
+  int init_tiles();
+  // tables ------------------------------------------------------------------
+  int tile_tables(int logn, const C** tw /*[JTB_MAX_STAGES]*/, const C** rtw);
+  int fs_tables(int logN, const C** A, const C** B, int* logL);
+  int blue_tables(i64 n, const C** bk1, const C** bk2, i64* M);
+  int dct_table(i64 n, const C** dtw);
+
+  // power-of-two c2c on lines [l0, l1) (tile kernel or four-step).  `in` and `out` may alias when
+  // gi == go (in place).
+  int c2c_pow2(const C* in, const Geo& gi, C* out, const Geo& go, i64 l0, i64 l1, int logn, const Fuse<T>& f,
+               int pro = PRO_DIRECT, int epi = EPI_DIRECT);
+  int tile_call(const C* in, const Geo& gi, C* out, const Geo& go, i64 l0, i64 l1, int logn, TileParams<T>& p);
+  // any-length in-place c2c on a batch of lines
+  int c2c_lines(C* a, const Geo& g, i64 nlines, i64 n, bool inverse, bool has_scale, T scale);
+  // real <-> packed half spectrum (1-D rule of fft/DoubleFFT_1D.java), lines of n reals, geometry in REAL units
+  int real_forward_lines(T* a, const Geo& g, i64 nlines, i64 n);
+  int real_inverse_lines(T* a, const Geo& g, i64 nlines, i64 n, bool scale);
+  // DCT/DST/DHT along lines (geometry in real units). kind: 1 DCT, 2 DST, 3 DHT
+  int r2r_lines(T* a, const Geo& g, i64 nlines, i64 n, int kind, bool inverse, bool scale);
+};
+
+extern template struct Engine<double>;
+extern template struct Engine<float>;
+
+}  // namespace jtb

@@ -1,0 +1,137 @@
+"""CPU-only parity run of the library's REAL kernel sources through the g++ CUDA-semantics shim
+(tests/emu).  This checks index math, packed layouts, fusions and host logic without a GPU; the GPU
+suite (tests/test_gpu_parity.py) repeats the same cases through the nvcc-built libjtb200.so.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import parity_cases as pc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU_LIB = os.path.join(HERE, "emu", "_build", "libjtb200_emu.so")
+
+
+@pytest.fixture(scope="module")
+def jt():
+    subprocess.run(["sh", os.path.join(HERE, "emu", "build_emu.sh")], check=True, capture_output=True)
+    import jtransforms_b200 as m
+    from jtransforms_b200 import _lib
+    _lib.use(EMU_LIB)
+    yield m
+    _lib.get().jtb_debug_set_limits(0, 0)
+    _lib._lib = None
+
+
+@pytest.fixture
+def small_limits(jt):
+    """force the two-pass (four-step) path at sizes the emulator handles quickly"""
+    from jtransforms_b200 import _lib
+    _lib.get().jtb_debug_set_limits(5, 3)
+    yield
+    _lib.get().jtb_debug_set_limits(0, 0)
+
+
+@pytest.mark.parametrize("prec", ["Double", "Float"])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 12, 13, 16, 32, 64, 100, 120, 128, 211, 256, 310, 512])
+def test_fft1d_complex(jt, prec, n):
+    pc.fft1d_complex(jt, prec, n)
+
+
+def test_fft1d_offset(jt):
+    pc.fft1d_complex(jt, "Double", 64, offa=6)
+    pc.fft1d_complex(jt, "Double", 30, offa=3)
+
+
+@pytest.mark.parametrize("prec", ["Double", "Float"])
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 8, 9, 16, 30, 64, 101, 128, 256])
+def test_fft1d_real(jt, prec, n):
+    pc.fft1d_real(jt, prec, n)
+
+
+@pytest.mark.parametrize("n", [64, 128, 256, 1024])
+def test_fft1d_two_pass(jt, small_limits, n):
+    pc.fft1d_complex(jt, "Double", n)
+    pc.fft1d_batch(jt, "Float", n, 3, pad=4)
+
+
+@pytest.mark.parametrize("n", [100, 311])
+def test_fft1d_bluestein_two_pass(jt, small_limits, n):
+    pc.fft1d_complex(jt, "Double", n)
+    pc.fft1d_real(jt, "Double", n)
+
+
+def test_fft1d_batch(jt):
+    pc.fft1d_batch(jt, "Double", 64, 5)
+    pc.fft1d_batch(jt, "Float", 17, 4, pad=2)
+
+
+@pytest.mark.parametrize("prec", ["Double", "Float"])
+@pytest.mark.parametrize("dims", [(2, 2), (4, 8), (16, 4), (5, 6), (12, 7), (32, 32), (3, 16)])
+def test_fft2d_complex(jt, prec, dims):
+    pc.fftnd_complex(jt, prec, dims)
+
+
+@pytest.mark.parametrize("dims", [(2, 2), (2, 8), (8, 2), (4, 16), (16, 16), (32, 8)])
+def test_fft2d_real(jt, dims):
+    pc.fftnd_real(jt, "Double", dims)
+    pc.fftnd_real_full(jt, "Double", dims)
+
+
+def test_fft2d_real_full_nonpow2(jt):
+    pc.fftnd_real_full(jt, "Double", (6, 10))
+
+
+def test_fft2d_two_pass(jt, small_limits):
+    pc.fftnd_complex(jt, "Double", (64, 16))
+    pc.fftnd_complex(jt, "Double", (16, 128))
+    pc.fftnd_real(jt, "Double", (32, 64))
+
+
+@pytest.mark.parametrize("dims", [(2, 2, 2), (4, 4, 8), (8, 2, 4), (3, 5, 4), (16, 8, 4)])
+def test_fft3d_complex(jt, dims):
+    pc.fftnd_complex(jt, "Double", dims)
+
+
+@pytest.mark.parametrize("dims", [(2, 2, 2), (4, 4, 8), (8, 4, 2), (2, 8, 4), (8, 8, 8)])
+def test_fft3d_real(jt, dims):
+    pc.fftnd_real(jt, "Double", dims)
+    pc.fftnd_real_full(jt, "Double", dims)
+
+
+def test_fft3d_two_pass(jt, small_limits):
+    pc.fftnd_complex(jt, "Double", (32, 16, 8))
+
+
+@pytest.mark.parametrize("kind", ["DCT", "DST", "DHT"])
+@pytest.mark.parametrize("dims", [(2,), (8,), (16,), (9,), (30,), (64,), (4, 8), (6, 5), (16, 16), (4, 2, 8), (3, 4, 5)])
+def test_r2r(jt, kind, dims):
+    pc.r2r(jt, "Double", kind, dims)
+
+
+@pytest.mark.parametrize("kind", ["DCT", "DST", "DHT"])
+def test_r2r_float(jt, kind):
+    pc.r2r(jt, "Float", kind, (32,))
+    pc.r2r(jt, "Float", kind, (8, 16))
+
+
+def test_errors(jt):
+    with pytest.raises(ValueError, match="greater than 0"):
+        jt.DoubleFFT_1D(0)
+    with pytest.raises(ValueError, match="greater than 1"):
+        jt.DoubleFFT_2D(1, 8)
+    with pytest.raises(ValueError, match="greater than 1"):
+        jt.DoubleFFT_3D(4, 1, 8)
+    with pytest.raises(ValueError, match="power of two"):
+        jt.DoubleFFT_2D(6, 8).realForward(np.zeros(48))
+    with pytest.raises(ValueError, match="power of two"):
+        jt.DoubleFFT_3D(4, 6, 8).realInverse(np.zeros(4 * 6 * 8), True)
+    with pytest.raises(IndexError):
+        jt.DoubleFFT_1D(16).complexForward(np.zeros(16))
+    with pytest.raises(ValueError):
+        jt.DoubleFFT_1D(16).complexForward(np.zeros(32, dtype=np.float32))
+    a = np.array([3.0, 4.0])
+    jt.DoubleFFT_1D(1).complexForward(a)       # n == 1 is a no-op
+    assert a.tolist() == [3.0, 4.0]
