@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of jtransforms_b200 (contract: see the task statement / DESIGN.md).
+
+Default workload = BASELINE.json's target configuration: DoubleFFT_3D.complexForward on 512^3 complex
+doubles (2 GiB, in place).  One "step" = one transform.  With N ranks the SAME transform is slab-decomposed
+over the N GPUs (scaling = "strong") with an all-to-all over NVLink.
+
+  python bench.py --gpus 1 --steps 20 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus 8 --steps 20 --warmup 3
+  python bench.py --impl reference ...      # the reference algorithm on the host cores (CPU arm)
+
+Other configurations of BASELINE.json can be timed with --workload {fft1d_2p20, fft2d_real_4096,
+bluestein_f32, dct2d_8192, fft3d_512}; they are reported in the same JSON shape.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "fft_gflops_5NlogN"
+UNIT = "GFLOP/s"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------- workloads
+class Workload:
+    """name, total points, flops per transform (5 N log2 N complex / 2.5 N log2 N real), element counts"""
+
+    def __init__(self, name):
+        self.name = name
+        if name == "fft3d_512":
+            self.dims, self.prec, self.kind, self.op = (512, 512, 512), "f64", "fft", "complexForward"
+            self.N = 512 ** 3
+            self.flops = 5.0 * self.N * math.log2(self.N)
+            self.elems = 2 * self.N
+            self.desc = "DoubleFFT_3D.complexForward 512^3 (2 GiB, in place)"
+            self.sweeps = 3
+        elif name == "fft1d_2p20":
+            self.dims, self.prec, self.kind, self.op = (1 << 20,), "f64", "fft", "complexForward"
+            self.N = 1 << 20
+            self.flops = 5.0 * self.N * 20
+            self.elems = 2 * self.N
+            self.desc = "DoubleFFT_1D.complexForward n=2^20"
+            self.sweeps = 2
+        elif name == "fft2d_real_4096":
+            self.dims, self.prec, self.kind, self.op = (4096, 4096), "f64", "fft", "realForward"
+            self.N = 4096 * 4096
+            self.flops = 2.5 * self.N * 24
+            self.elems = self.N
+            self.desc = "DoubleFFT_2D.realForward 4096x4096"
+            self.sweeps = 2
+        elif name == "dct2d_8192":
+            self.dims, self.prec, self.kind, self.op = (8192, 8192), "f64", "dct", "forward"
+            self.N = 8192 * 8192
+            self.flops = 2.5 * self.N * 26
+            self.elems = self.N
+            self.desc = "DoubleDCT_2D.forward(scale=true) 8192x8192"
+            self.sweeps = 2
+        elif name == "bluestein_f32":
+            self.dims, self.prec, self.kind, self.op = (1000003,), "f32", "fft", "complexForward"
+            self.batch = 64
+            self.N = 1000003
+            self.flops = 5.0 * self.N * math.log2(self.N) * self.batch
+            self.elems = 2 * self.N * self.batch
+            self.desc = "FloatFFT_1D.complexForward n=1000003 (Bluestein) x batch 64 per GPU"
+            self.sweeps = 4
+        else:
+            raise SystemExit("unknown workload " + name)
+        self.esize = 8 if self.prec == "f64" else 4
+        self.bytes = self.elems * self.esize
+
+
+# ------------------------------------------------------------------------------- clocks sampler
+class Clocks(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples = index, False, []
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [s.strip() for s in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None,
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------- CPU arm
+def cpu_reference(w: Workload, budget_s: float = 20.0):
+    """Reference algorithm on the host cores.  kind = "reference" when oracle/_ref (the reference compiled
+    here) exists, else "port": the oracle's restatement (SciPy pocketfft C++ kernels, all host threads)."""
+    import numpy as np
+    import scipy.fft as sfft
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(2)
+    if w.name == "fft3d_512":
+        shape = (256, 512, 512)      # half of the slices: bounded sample, same row/column lengths
+        x = (rng.random(shape) + 1j * rng.random(shape))
+        fn = lambda: sfft.fftn(x, workers=cores)
+        n = float(np.prod(shape))
+        flops = 5.0 * n * math.log2(n)
+        sample = "256x512x512 complex128 (half of the slices), scipy.fft.fftn workers=%d" % cores
+    elif w.name == "fft1d_2p20":
+        x = rng.random(1 << 20) + 1j * rng.random(1 << 20)
+        fn = lambda: sfft.fft(x, workers=cores)
+        flops, sample = w.flops, "full size, scipy.fft.fft"
+    elif w.name == "fft2d_real_4096":
+        x = rng.random((4096, 4096))
+        fn = lambda: sfft.rfft2(x, workers=cores)
+        flops, sample = w.flops, "full size, scipy.fft.rfft2 workers=%d" % cores
+    elif w.name == "dct2d_8192":
+        x = rng.random((4096, 8192))
+        fn = lambda: sfft.dctn(x, type=2, norm="ortho", workers=cores)
+        n = float(x.size)
+        flops, sample = 2.5 * n * math.log2(n), "4096x8192 (half the rows), scipy.fft.dctn workers=%d" % cores
+    else:
+        x = (rng.random((4, 1000003)) + 1j * rng.random((4, 1000003))).astype(np.complex64)
+        fn = lambda: sfft.fft(x, axis=-1, workers=cores)
+        flops = 5.0 * 1000003 * math.log2(1000003) * 4
+        sample = "4 transforms of n=1000003 complex64, scipy.fft.fft workers=%d" % cores
+    fn()
+    best, t_used, reps = 1e30, 0.0, 0
+    while t_used < budget_s and reps < 5:
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        best = min(best, dt)
+        t_used += dt
+        reps += 1
+    return {"value": flops / best / 1e9, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+            "seconds": best}
+
+
+def run_reference_arm(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_reference(w, budget_s=30.0)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["seconds"] * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": w.prec, "data": "synthetic",
+            "config": {"workload": w.desc, "note": "CPU arm: bounded sample, " + base["sample"]},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="jtb200")
+    ap.add_argument("--workload", default="fft3d_512")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    w = Workload(args.workload)
+    if args.impl == "reference":
+        run_reference_arm(args, w)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import jtransforms_b200 as jt
+    from jtransforms_b200 import _lib
+    from jtransforms_b200.dist import SlabFFT3D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.get()
+    hbm_peak, peak_kind = peaks()
+    tdt = torch.float64 if w.prec == "f64" else torch.float32
+    prec = _lib.F64 if w.prec == "f64" else _lib.F32
+
+    def fill(t, seed):
+        _lib.check(lib.jtb_fill_uniform_device(prec, local, C.c_void_p(t.data_ptr()), t.numel(), seed, 0.0, 1.0,
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sharded = w.name == "fft3d_512" and world > 1
+    if world > 1 and not sharded and w.name != "bluestein_f32":
+        raise SystemExit("workload %s does not shard: replicas only (run with --gpus 1)" % w.name)
+
+    # ---- set up the step closure (device resident) and the e2e closure (host buffers)
+    if w.name == "fft3d_512":
+        S, R, Cn = w.dims
+        slab = SlabFFT3D(S, R, Cn, prec, device_index=local)
+        a = torch.empty(slab.local_elements(), dtype=tdt, device=dev)
+        work = torch.empty_like(a) if world > 1 else None
+        fill(a, 2 + rank * a.numel())
+        step = lambda: slab.forward(a, work)
+        local_bytes = a.numel() * w.esize
+    else:
+        klass = {"fft1d_2p20": jt.DoubleFFT_1D, "fft2d_real_4096": jt.DoubleFFT_2D, "dct2d_8192": jt.DoubleDCT_2D,
+                 "bluestein_f32": jt.FloatFFT_1D}[w.name]
+        plan = klass(*w.dims, device=local)
+        a = torch.empty(w.elems, dtype=tdt, device=dev)
+        fill(a, 2)
+        if w.name == "bluestein_f32":
+            step = lambda: plan.complexForwardBatch(a, w.batch, 2 * w.N)
+        elif w.name == "dct2d_8192":
+            step = lambda: plan.forward(a, True)
+        elif w.name == "fft2d_real_4096":
+            step = lambda: plan.realForward(a)
+        else:
+            step = lambda: plan.complexForward(a)
+        local_bytes = a.numel() * w.esize
+
+    refill_every = 40     # repeated in-place forward transforms grow by sqrt(N) per step: refill before overflow
+    seed0 = 2 + rank * a.numel()
+
+    for i in range(args.warmup):
+        step()
+    fill(a, seed0)
+    barrier()
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    l0 = lib.jtb_launch_count(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        if i and i % refill_every == 0:
+            fill(a, seed0)
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.jtb_launch_count(local) - l0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    total_flops = w.flops * (world if w.name == "bluestein_f32" else 1)
+    value = total_flops / (ms_per_step * 1e-3) / 1e9
+
+    # ---- per-pass roofline of the dominant kernel (fft_tile_kernel), CUDA events on the launching stream
+    roof = None
+    if w.name == "fft3d_512" and world == 1:
+        S, R, Cn = w.dims
+        passes = [("k3 rows (contiguous)", (Cn, S * R, 1, 0, Cn, 1)),
+                  ("k2 columns (stride C)", (R, Cn * S, Cn, 1, R * Cn, Cn)),
+                  ("k1 slices (stride R*C)", (S, R * Cn, R * Cn, 1, S * R * Cn, R * Cn))]
+        per = []
+        for name, (n, nl, c0, d0, d3, st) in passes:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            reps = 5
+            slab._lines(a, n, nl, c0, d0, d3, st)
+            torch.cuda.synchronize()
+            ev[0].record()
+            for _ in range(reps):
+                slab._lines(a, n, nl, c0, d0, d3, st)
+            ev[1].record()
+            torch.cuda.synchronize()
+            t_ms = ev[0].elapsed_time(ev[1]) / reps
+            per.append({"pass": name, "ms": t_ms, "GBps": 2 * local_bytes / (t_ms * 1e-3) / 1e9})
+        worst = max(per, key=lambda p: p["ms"])
+        roof = {"bound": "hbm", "kernel": "fft_tile_kernel<double,9> " + worst["pass"], "achieved": worst["GBps"],
+                "peak": hbm_peak, "peak_source": peak_kind, "unit": "GB/s", "frac": worst["GBps"] / hbm_peak,
+                "traffic": None, "algorithmic_bytes_per_launch": 2 * local_bytes, "passes": per}
+    else:
+        # whole-step model: `sweeps` read+write passes over the working set
+        algo = 2.0 * w.sweeps * local_bytes
+        gbps = algo / (ms_per_step * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "whole step (%d-sweep model)" % w.sweeps, "achieved": gbps, "peak": hbm_peak,
+                "peak_source": peak_kind, "unit": "GB/s", "frac": gbps / hbm_peak, "traffic": None,
+                "algorithmic_bytes_per_launch": algo}
+
+    # ---- end to end: pinned host array in, host array out, through the public API
+    e2e = None
+    esteps = max(1, min(args.e2e_steps, args.steps))
+    if w.name == "fft3d_512":
+        S, R, Cn = w.dims
+        if world == 1:
+            hp = C.c_void_p()
+            _lib.check(lib.jtb_host_alloc(C.byref(hp), w.bytes))
+            harr = np.ctypeslib.as_array((C.c_double * w.elems).from_address(hp.value))
+            harr[:] = 0.5
+            f3 = jt.DoubleFFT_3D(S, R, Cn, device=local)
+            f3.complexForward(harr)
+            harr[:] = 0.25
+            t0 = time.perf_counter()
+            for _ in range(esteps):
+                f3.complexForward(harr)
+            dt = (time.perf_counter() - t0) / esteps
+            h2d = d2h = w.bytes
+            lib.jtb_host_free(hp)
+        else:
+            hin = torch.full((slab.local_elements(),), 0.25, dtype=tdt).pin_memory()
+            hout = torch.empty(w.elems // world, dtype=tdt).pin_memory()
+
+            def e2e_step():
+                a.copy_(hin, non_blocking=True)
+                res = slab.forward(a, work)
+                hout.copy_(res.view(-1), non_blocking=True)
+                torch.cuda.synchronize()
+            e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(esteps):
+                e2e_step()
+            barrier()
+            dt = (time.perf_counter() - t0) / esteps
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+            h2d = d2h = w.bytes // world
+        e2e = {"value": w.flops / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": dt * 1e3, "steps": esteps}
+    else:
+        hp = C.c_void_p()
+        _lib.check(lib.jtb_host_alloc(C.byref(hp), w.bytes))
+        ct = C.c_double if w.prec == "f64" else C.c_float
+        harr = np.ctypeslib.as_array((ct * w.elems).from_address(hp.value))
+        harr[:] = 0.25
+
+        def e2e_step():
+            if w.name == "bluestein_f32":
+                plan.complexForwardBatch(harr, w.batch, 2 * w.N)
+            elif w.name == "dct2d_8192":
+                plan.forward(harr, True)
+            elif w.name == "fft2d_real_4096":
+                plan.realForward(harr)
+            else:
+                plan.complexForward(harr)
+        e2e_step()
+        harr[:] = 0.25
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            e2e_step()
+        dt = (time.perf_counter() - t0) / esteps
+        lib.jtb_host_free(hp)
+        e2e = {"value": total_flops / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": w.bytes,
+               "d2h_bytes_per_step": w.bytes, "ms_per_step": dt * 1e3, "steps": esteps}
+
+    clk = None
+    if rank == 0:
+        clocks.stop_flag = True
+        clocks.join(timeout=2)
+        clk = clocks.summary()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_reference(w)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak" if w.name == "bluestein_f32" else "strong", "vs_baseline": None, "dtype": w.prec,
+                "data": "synthetic",
+                "config": {"workload": w.desc, "l2": "working set %.0f MiB per GPU >> 126 MB L2, no flush needed"
+                           % (local_bytes / 2 ** 20) if local_bytes > 400e6 else
+                           "working set %.0f MiB per GPU (L2-resident; as in the reference's repeated-call benchmark)"
+                           % (local_bytes / 2 ** 20),
+                           "parallelism": "slab%d" % world if sharded else "single"},
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

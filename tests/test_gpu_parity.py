@@ -1,0 +1,158 @@
+"""GPU parity suite: the nvcc-built libjtb200.so, called through the C ABI (ctypes), against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import parity_cases as pc
+from oracle import jt_oracle as o
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+FFTW = os.path.join(HERE, "golden", "fftw")
+
+
+@pytest.fixture(scope="module")
+def jt():
+    import jtransforms_b200 as m
+    from jtransforms_b200 import _lib
+    _lib._lib = None
+    lib = _lib.get()            # raises if libjtb200.so is missing: no fallback
+    assert lib.jtb_device_count() >= 1
+    lib.jtb_debug_set_limits(0, 0)
+    return m
+
+
+def _sizes():
+    with open(os.path.join(FFTW, "sizes.txt")) as f:
+        return [int(s) for s in f.read().split()]
+
+
+@pytest.mark.parametrize("n", _sizes())
+def test_fftw_golden(jt, n):
+    """src/test/java/org/jtransforms/fft/DoubleFFT_1DTest.java:208-219 and FloatFFT_1DTest.java:203"""
+    x = np.fromfile(os.path.join(FFTW, "fftw%d.in" % n), dtype="<f8")
+    want = np.fromfile(os.path.join(FFTW, "fftw%d.out" % n), dtype="<f8")
+    a = x.copy()
+    jt.DoubleFFT_1D(n).complexForward(a)
+    pc.check(a, want, "Double", n, "fftw %d" % n)
+    assert o.rmse(a, want) <= 1e-12 * max(1.0, np.sqrt(n))
+    b = x.astype(np.float32)
+    jt.FloatFFT_1D(n).complexForward(b)
+    pc.check(b, want, "Float", n, "fftw float %d" % n)
+
+
+@pytest.mark.parametrize("prec", ["Double", "Float"])
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 16, 100, 120, 211, 310, 512, 1024, 4096, 8192, 16384, 65536, 10158,
+                               65530, 1 << 20, 1 << 21])
+def test_fft1d_complex(jt, prec, n):
+    pc.fft1d_complex(jt, prec, n)
+
+
+@pytest.mark.parametrize("prec", ["Double", "Float"])
+@pytest.mark.parametrize("n", [2, 4, 5, 9, 64, 101, 1024, 4096, 16384, 32768, 65536, 100000])
+def test_fft1d_real(jt, prec, n):
+    pc.fft1d_real(jt, prec, n)
+
+
+def test_fft1d_bluestein_prime_batch(jt):
+    """config 3 (reduced batch): FloatFFT_1D, n = 1 000 003 (prime), Bluestein"""
+    pc.fft1d_batch(jt, "Float", 1000003, 3, pad=2)
+    pc.fft1d_complex(jt, "Double", 1000003)
+
+
+def test_fft1d_batch(jt):
+    pc.fft1d_batch(jt, "Double", 4096, 37)
+    pc.fft1d_batch(jt, "Float", 1 << 15, 5, pad=6)
+    pc.fft1d_batch(jt, "Double", 1000, 9)
+
+
+@pytest.mark.parametrize("prec", ["Double", "Float"])
+@pytest.mark.parametrize("dims", [(2, 2), (64, 128), (100, 120), (1024, 512), (4096, 64), (16, 8192), (311, 64)])
+def test_fft2d_complex(jt, prec, dims):
+    pc.fftnd_complex(jt, prec, dims)
+
+
+@pytest.mark.parametrize("dims", [(2, 2), (2, 16), (16, 2), (256, 512), (1024, 64), (4096, 4096)])
+def test_fft2d_real(jt, dims):
+    """config 2 at full size is the last case"""
+    pc.fftnd_real(jt, "Double", dims)
+
+
+def test_fft2d_real_misc(jt):
+    pc.fftnd_real(jt, "Float", (128, 256))
+    pc.fftnd_real_full(jt, "Double", (64, 32))
+    pc.fftnd_real_full(jt, "Double", (30, 50))
+
+
+@pytest.mark.parametrize("prec", ["Double", "Float"])
+@pytest.mark.parametrize("dims", [(2, 2, 2), (64, 64, 64), (16, 32, 128), (12, 10, 14), (128, 256, 64)])
+def test_fft3d_complex(jt, prec, dims):
+    pc.fftnd_complex(jt, prec, dims)
+
+
+def test_fft3d_real(jt):
+    pc.fftnd_real(jt, "Double", (32, 64, 16))
+    pc.fftnd_real(jt, "Double", (2, 4, 8))
+    pc.fftnd_real_full(jt, "Double", (8, 16, 32))
+    pc.fftnd_real_full(jt, "Float", (6, 10, 12))
+
+
+def test_fft3d_512_properties(jt):
+    """config 5 at full size, device resident: spot bins against direct sums, Parseval, round trip"""
+    import torch
+    S = R = C = 512
+    N = S * R * C
+    lib = __import__("jtransforms_b200")._lib.get()
+    a = torch.empty(2 * N, dtype=torch.float64, device="cuda:0")
+    import ctypes
+    assert lib.jtb_fill_uniform_device(0, 0, ctypes.c_void_p(a.data_ptr()), 2 * N, 2, 0.0, 1.0, None) == 0
+    torch.cuda.synchronize()
+    x = a.clone()
+    # the device fill equals the oracle's counter-based generator bit for bit
+    assert np.array_equal(x[:4096].cpu().numpy(), o.fill_uniform(4096, seed=2))
+    f = jt.DoubleFFT_3D(S, R, C)
+    f.complexForward(a)
+    torch.cuda.synchronize()
+    e_in = float((x * x).sum())
+    e_out = float((a * a).sum())
+    assert abs(e_out / (N * e_in) - 1.0) < 1e-12
+    xc = torch.view_as_complex(x.view(-1, 2)).view(S, R, C)
+    ac = torch.view_as_complex(a.view(-1, 2)).view(S, R, C)
+    rng = np.random.default_rng(5)
+    for _ in range(4):
+        k1, k2, k3 = (int(v) for v in rng.integers(0, 512, 3))
+        w1 = torch.exp(-2j * np.pi * k1 * torch.arange(S, device="cuda:0", dtype=torch.float64) / S)
+        w2 = torch.exp(-2j * np.pi * k2 * torch.arange(R, device="cuda:0", dtype=torch.float64) / R)
+        w3 = torch.exp(-2j * np.pi * k3 * torch.arange(C, device="cuda:0", dtype=torch.float64) / C)
+        want = torch.einsum("srt,s,r,t->", xc, w1, w2, w3)
+        got = ac[k1, k2, k3]
+        assert abs(complex(got - want)) <= 1e-12 * 27 * float(torch.sqrt(torch.tensor(e_in * N) / N)) * 10
+    f.complexInverse(a, True)
+    torch.cuda.synchronize()
+    err = float(torch.linalg.norm(a - x) / torch.linalg.norm(x))
+    assert err <= 1e-12 * 27
+
+
+@pytest.mark.parametrize("kind", ["DCT", "DST", "DHT"])
+@pytest.mark.parametrize("dims", [(2,), (16,), (30,), (1024,), (8192,), (65536,), (1000,), (256, 256), (100, 60),
+                                  (2048, 1024), (16, 32, 64), (5, 6, 7)])
+def test_r2r(jt, kind, dims):
+    pc.r2r(jt, "Double", kind, dims)
+
+
+@pytest.mark.parametrize("kind", ["DCT", "DST", "DHT"])
+def test_r2r_float(jt, kind):
+    pc.r2r(jt, "Float", kind, (4096,))
+    pc.r2r(jt, "Float", kind, (128, 512))
+
+
+def test_dct2d_8192(jt):
+    """config 4 at full size (DCT; DST/DHT share every kernel and are covered at 2048x1024 above)"""
+    import scipy.fft as sfft
+    n = 8192
+    x = o.fill_uniform(n * n, seed=2)
+    a = x.copy()
+    jt.DoubleDCT_2D(n, n).forward(a, True)
+    want = sfft.dctn(x.reshape(n, n), type=2, norm="ortho", workers=-1).ravel()
+    pc.check(a, want, "Double", n * n, "DCT 8192^2")
