@@ -11,6 +11,7 @@
 #pragma once
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 #include "jtb_engine.h"
 
@@ -164,6 +165,10 @@ int Engine<T>::tile_call(const C* in, const Geo& gi, C* out, const Geo& go, i64 
   int W;
   if (wf || p.epi == EPI_REMAP) W = (int)(128 / sizeof(C));      // 128-byte segments across adjacent lines
   else W = 256 / ti.tpl;
+  {
+    const char* ev = getenv(wf ? "JTB_W_STRIDED" : (p.epi == EPI_REMAP ? "JTB_W_REMAP" : "JTB_W_CONTIG"));
+    if (ev && atoi(ev) > 0) W = atoi(ev);
+  }
   if (W > ti.maxt / ti.tpl) W = ti.maxt / ti.tpl;
   const bool need_smem = ti.nstages > 1 || staged;
   if (need_smem) while (W > 1 && (size_t)W * line_bytes > (size_t)227 * 1024) W >>= 1;
@@ -305,6 +310,10 @@ int Engine<T>::c2c_pow2(const C* in, const Geo& gi, C* out, const Geo& go, i64 l
   return ST_OK;
 }
 
+template <typename T>
+int fast_c2c(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, int logn, bool inverse, bool has_scale, T scale,
+             bool* handled);   // jtb_fast.cu
+
 // ---------------------------------------------------------------------------------- any-length c2c
 template <typename T>
 int Engine<T>::c2c_lines(C* a, const Geo& g, i64 nlines, i64 n, bool inverse, bool has_scale, T scale) {
@@ -314,6 +323,9 @@ int Engine<T>::c2c_lines(C* a, const Geo& g, i64 nlines, i64 n, bool inverse, bo
     return ST_OK;
   }
   if (is_pow2(n)) {
+    bool handled = false;
+    JTB_TRY(fast_c2c<T>(*this, a, g, nlines, ilog2(n), inverse, has_scale, scale, &handled));
+    if (handled) return ST_OK;
     Fuse<T> f;
     f.swap_in = inverse; f.swap_out = inverse;
     f.has_scale = has_scale; f.scale = scale;

@@ -1,0 +1,130 @@
+// Instantiations and host-side dispatch of fft_fast_kernel (jtb_fast.cuh).
+#include <cstdlib>
+
+#include "jtb_engine_impl.cuh"
+#include "jtb_fast.cuh"
+
+namespace jtb {
+
+namespace {
+
+template <typename T> struct FastEntry {
+  int logn, loge, strided, W, threads, smem, twcount, nstages;
+  int bits[JTB_MAX_STAGES];
+  void (*kern)(const FastParams<T>);
+  bool attr_done;
+};
+
+template <typename T, int LOGN, int LOGE, bool STRIDED, int W> FastEntry<T> make_entry() {
+  typedef Sched<LOGN, LOGE> S;
+  FastEntry<T> e;
+  e.logn = LOGN; e.loge = LOGE; e.strided = STRIDED; e.W = W; e.threads = W * S::TPL;
+  e.twcount = FastTw<S>::COUNT;
+  e.smem = (int)((FastAddr<T, S, STRIDED, W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
+  e.nstages = S::S;
+  for (int s = 0; s < JTB_MAX_STAGES; ++s) e.bits[s] = s < S::S ? S::bits(s) : 0;
+  e.kern = fft_fast_kernel<T, LOGN, LOGE, STRIDED, W>;
+  e.attr_done = false;
+  return e;
+}
+
+template <typename T> std::vector<FastEntry<T>>& registry();
+
+template <> std::vector<FastEntry<double>>& registry<double>() {
+  static std::vector<FastEntry<double>> r = {
+      // first entry of each (logn, layout) is the default; the others are tuning variants (JTB_FAST_W)
+      make_entry<double, 9, 3, true, 8>(),  make_entry<double, 9, 3, true, 4>(),
+      make_entry<double, 9, 3, false, 4>(), make_entry<double, 9, 3, false, 2>(), make_entry<double, 9, 3, false, 1>(),
+      make_entry<double, 9, 3, false, 8>(),
+      make_entry<double, 6, 3, true, 8>(),  make_entry<double, 6, 3, true, 16>(), make_entry<double, 6, 3, true, 32>(),
+      make_entry<double, 6, 3, false, 16>(), make_entry<double, 6, 3, false, 32>(),
+      make_entry<double, 10, 4, true, 8>(), make_entry<double, 10, 4, true, 4>(),
+      make_entry<double, 10, 4, false, 4>(), make_entry<double, 10, 4, false, 2>(),
+      make_entry<double, 12, 4, false, 1>(), make_entry<double, 12, 4, false, 2>(),
+      make_entry<double, 11, 4, false, 2>(), make_entry<double, 11, 4, false, 4>(),
+  };
+  return r;
+}
+template <> std::vector<FastEntry<float>>& registry<float>() {
+  static std::vector<FastEntry<float>> r = {
+      make_entry<float, 9, 3, true, 16>(),  make_entry<float, 9, 3, true, 8>(),
+      make_entry<float, 9, 3, false, 4>(),  make_entry<float, 9, 3, false, 2>(),
+      make_entry<float, 10, 4, true, 16>(), make_entry<float, 10, 4, true, 8>(),
+      make_entry<float, 10, 4, false, 4>(), make_entry<float, 10, 4, false, 2>(),
+      make_entry<float, 11, 4, true, 8>(),
+      make_entry<float, 11, 4, false, 2>(), make_entry<float, 11, 4, false, 4>(),
+  };
+  return r;
+}
+
+template <typename T> int fast_table(Engine<T>& e, const FastEntry<T>& f, const cx<T>** out) {
+  typedef cx<T> C;
+  const std::string key = mkkey("ftw", e.pname(), f.logn, f.loge);
+  void* d = e.ctx->table(key);
+  if (!d) {
+    std::vector<C> h((size_t)(f.twcount > 0 ? f.twcount : 1));
+    i64 ns = 1;
+    size_t o = 0;
+    for (int s = 0; s < f.nstages; ++s) {
+      const i64 R = 1LL << f.bits[s];
+      if (s > 0)
+        for (int j = 0; j < f.bits[s]; ++j)
+          for (i64 k = 0; k < ns; ++k) h[o++] = unit_root<T>((1LL << j) * k, ns * R);
+      ns *= R;
+    }
+    JTB_TRY(e.ctx->put_table(key, h.data(), h.size() * sizeof(C), &d));
+  }
+  *out = (const C*)d;
+  return ST_OK;
+}
+
+}  // namespace
+
+// Runs the lean kernel when the call is a plain in-place transform on a supported layout.
+// *handled = false (and ST_OK) when the caller must use the general tile kernel.
+template <typename T>
+int fast_c2c(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, int logn, bool inverse, bool has_scale, T scale,
+             bool* handled) {
+  *handled = false;
+  static const bool off = getenv("JTB_NO_FAST") != nullptr;
+  if (off || nlines <= 0) return ST_OK;
+  if (((uintptr_t)a % sizeof(cx<T>)) != 0) return ST_OK;
+  const i64 n = 1LL << logn;
+  bool strided;
+  if (g.stride == 1 && g.c[0] == 1 && g.c[1] == 1 && g.c[2] == 1) strided = false;
+  else if (g.stride > 1 && g.d[0] == 1 && g.c[1] == 1 && g.c[2] == 1 && g.c[0] > 1 &&
+           (n - 1) * g.stride + g.c[0] < 0x7fffffffLL && nlines % g.c[0] == 0) strided = true;
+  else return ST_OK;
+  const char* ev = getenv(strided ? "JTB_FAST_WS" : "JTB_FAST_WC");
+  const int wwant = ev ? atoi(ev) : 0;
+  FastEntry<T>* pick = nullptr;
+  for (auto& f : registry<T>()) {
+    if (f.logn != logn || (f.strided != 0) != strided) continue;
+    if (strided && (g.c[0] % f.W) != 0) continue;
+    if (wwant > 0 && f.W != wwant) continue;
+    pick = &f;
+    break;
+  }
+  if (!pick) return ST_OK;
+  if (!pick->attr_done) {
+    JTB_CUDA(cudaFuncSetAttribute(pick->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pick->smem));
+    pick->attr_done = true;
+  }
+  FastParams<T> p;
+  p.a = a; p.nlines = nlines;
+  p.line_dist = g.d[3]; p.c0 = (int)g.c[0]; p.stride = (int)g.stride;
+  p.inverse = inverse; p.has_scale = has_scale; p.scale = scale;
+  JTB_TRY(fast_table(e, *pick, &p.twg));
+  const i64 nblk = (nlines + pick->W - 1) / pick->W;
+  if (nblk > 0x7fffffffLL) return ST_OK;
+  JTB_LAUNCH(pick->kern, (unsigned)nblk, (unsigned)pick->threads, (size_t)pick->smem, e.st, p);
+  JTB_CUDA(cudaGetLastError());
+  e.ctx->launches++;
+  *handled = true;
+  return ST_OK;
+}
+
+template int fast_c2c<double>(Engine<double>&, double2*, const Geo&, i64, int, bool, bool, double, bool*);
+template int fast_c2c<float>(Engine<float>&, float2*, const Geo&, i64, int, bool, bool, float, bool*);
+
+}  // namespace jtb

@@ -1,0 +1,170 @@
+// Lean in-place line FFT kernel for the hot power-of-two lengths (the axis passes of DoubleFFT_2D/3D and
+// the batched 1-D transforms).  Same Stockham register/shared-memory structure as fft_tile_kernel
+// (jtb_tile.cuh) but with everything the hot path does not need stripped: 32-bit in-tile addressing,
+// compile-time line layout and lines-per-CTA, per-stage base twiddles w^(k), w^(2k), w^(4k).. staged in
+// shared memory with the remaining powers derived by multiplication, no fusion hooks except the
+// inverse (re<->im swap) and an output scale.
+//
+// Replaces, per line: utils/CommonUtils.java:708-793 (cftfsub/cftbsub) + bitrv2/bitrv2conj :824-2070;
+// per launch: the row/column/slice loops fft/DoubleFFT_2D.java:3100-3140, :3352-3529 and
+// fft/DoubleFFT_3D.java:5505-5713, :6318-6520.
+#pragma once
+#include "jtb_tile.cuh"
+
+namespace jtb {
+
+template <typename T> struct FastParams {
+  cx<T>* a;          // transformed in place
+  i64 nlines;
+  i64 line_dist;     // contiguous layout: distance between consecutive lines
+                     // strided layout: distance between groups of c0 adjacent lines
+  int c0;            // strided layout: number of adjacent lines (distance 1) per group
+  int stride;        // strided layout: distance between consecutive elements of a line
+  int inverse;
+  int has_scale;
+  T scale;
+  const cx<T>* twg;  // base twiddles, layout below (fast_twiddle_count entries)
+};
+
+// base twiddle table: for stage s >= 1 and j < bits(s):  tab[toff(s) + j*ns(s) + k] = exp(-2 pi i 2^j k / (ns(s) 2^bits(s)))
+template <typename S> struct FastTw {
+  __host__ __device__ static constexpr int toff(int s) { int o = 0; for (int i = 1; i < s; ++i) o += S::bits(i) * S::ns(i); return o; }
+  static constexpr int COUNT = toff(S::S);
+};
+
+template <typename T, typename S, bool STRIDED, int W> struct FastAddr {
+  static constexpr int LD = STRIDED ? S::N : S::LD;
+  static constexpr int TILE = STRIDED ? S::N * W : S::LD * W;
+  __device__ static __forceinline__ int at(int i, int w) {
+    if (STRIDED) return i * W + w;
+    return w * S::LD + i + (i >> S::LOGPAD);
+  }
+};
+
+template <typename T, typename S, int s, bool STRIDED, int W> struct FastStage {
+  static constexpr int LOGR = S::bits(s);
+  static constexpr int R = 1 << LOGR;
+  static constexpr int NB = S::E / R;
+  static constexpr int NS = S::ns(s);
+  typedef FastAddr<T, S, STRIDED, W> A;
+
+  __device__ static __forceinline__ void compute(cx<T>* v, int t, const cx<T>* twt) {
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+      cx<T> x[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) x[r] = v[m + r * NB];
+      if (s > 0) {
+        const int k = (t + m * S::TPL) & (NS - 1);
+        constexpr int TOFF = FastTw<S>::toff(s);
+        cx<T> tw[R];
+#pragma unroll
+        for (int j = 0; j < LOGR; ++j) tw[1 << j] = twt[TOFF + j * NS + k];
+#pragma unroll
+        for (int r = 3; r < R; ++r) {
+          // highest set bit h of r; r = 2^h + rest
+          const int h = (r >= 8) ? 8 : ((r >= 4) ? 4 : 2);
+          if (r != h) tw[r] = cmul(tw[h], tw[r - h]);
+        }
+#pragma unroll
+        for (int r = 1; r < R; ++r) x[r] = cmul(x[r], tw[r]);
+      }
+      Bfly<T, R>::run(x);
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[m + r * NB] = x[r];
+    }
+  }
+  __device__ static __forceinline__ void scatter(const cx<T>* v, cx<T>* sm, int t, int w) {
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+      const int jv = t + m * S::TPL;
+      const int k = jv & (NS - 1);
+      const int j0 = ((jv - k) << LOGR) + k;
+#pragma unroll
+      for (int r = 0; r < R; ++r) sm[A::at(j0 + r * NS, w)] = v[m + r * NB];
+    }
+  }
+};
+
+template <typename T, typename S, int s, bool STRIDED, int W> struct FastLoop {
+  typedef FastAddr<T, S, STRIDED, W> A;
+  __device__ static __forceinline__ void run(cx<T>* v, cx<T>* sm, const cx<T>* twt, int t, int w) {
+    FastStage<T, S, s, STRIDED, W>::compute(v, t, twt);
+    if (s + 1 < S::S) {
+      if (s > 0) __syncthreads();
+      FastStage<T, S, s, STRIDED, W>::scatter(v, sm, t, w);
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < S::E; ++q) v[q] = sm[A::at(t + q * S::TPL, w)];
+      FastLoop<T, S, (s + 1 < S::S ? s + 1 : s), STRIDED, W>::run(v, sm, twt, t, w);
+    }
+  }
+};
+
+template <int THREADS> struct FastOcc {   // resident CTAs per SM we compile for
+  static constexpr int MINB = THREADS >= 1024 ? 1 : (THREADS >= 512 ? 2 : (THREADS >= 256 ? 4 : (THREADS >= 128 ? 8 : 12)));
+};
+
+template <typename T, int LOGN, int LOGE, bool STRIDED, int W>
+__global__ void __launch_bounds__(W * Sched<LOGN, LOGE>::TPL, (Sched<LOGN, LOGE>::E <= 8 ? FastOcc<W * Sched<LOGN, LOGE>::TPL>::MINB
+                                                                                      : (FastOcc<W * Sched<LOGN, LOGE>::TPL>::MINB + 1) / 2))
+fft_fast_kernel(const FastParams<T> p) {
+  typedef Sched<LOGN, LOGE> S;
+  typedef cx<T> C;
+  typedef FastAddr<T, S, STRIDED, W> A;
+  JTB_DYN_SMEM(smem_raw);
+  C* sm = reinterpret_cast<C*>(smem_raw);
+  C* twt = sm + A::TILE;
+  const int tid = threadIdx.x;
+  int w, t;
+  if (STRIDED) { w = tid % W; t = tid / W; } else { t = tid % S::TPL; w = tid / S::TPL; }
+  for (int i = tid; i < FastTw<S>::COUNT; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
+
+  const i64 line0 = (i64)blockIdx.x * W;
+  C* base;
+  int es;
+  bool valid = true;
+  if (STRIDED) {
+    const i64 grp = line0 / p.c0;
+    const int c = (int)(line0 - grp * p.c0);
+    base = p.a + grp * p.line_dist + c + w;
+    es = p.stride;
+  } else {
+    valid = line0 + w < p.nlines;
+    base = p.a + (valid ? (line0 + w) * p.line_dist : 0);
+    es = 1;
+  }
+  C v[S::E];
+  if (valid) {
+#pragma unroll
+    for (int q = 0; q < S::E; ++q) v[q] = base[(t + q * S::TPL) * es];
+  } else {
+#pragma unroll
+    for (int q = 0; q < S::E; ++q) v[q] = mk<T>(0, 0);
+  }
+  if (p.inverse) {
+#pragma unroll
+    for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
+  }
+  FastLoop<T, S, 0, STRIDED, W>::run(v, sm, twt, t, w);
+  if (p.has_scale) {
+#pragma unroll
+    for (int q = 0; q < S::E; ++q) { v[q].x *= p.scale; v[q].y *= p.scale; }
+  }
+  if (p.inverse) {
+#pragma unroll
+    for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
+  }
+  if (valid) {
+#pragma unroll
+    for (int q = 0; q < S::E; ++q) base[(t + q * S::TPL) * es] = v[q];
+  }
+}
+
+// host-side description of one instantiation
+struct FastInfo {
+  int logn, loge, strided, W, threads, smem_bytes, tw_count;
+  int nstages, bits[JTB_MAX_STAGES];
+};
+
+}  // namespace jtb

@@ -23,12 +23,12 @@ template <int LOGN, int LOGE> struct Sched {
   static constexpr int S = (LOGN <= LOGE) ? 1 : (LOGN + LOGE - 1) / LOGE;
   static constexpr int BASE = LOGN / S;
   static constexpr int REM = LOGN % S;
-  static constexpr int bits(int s) { return BASE + (s < REM ? 1 : 0); }
+  __host__ __device__ static constexpr int bits(int s) { return BASE + (s < REM ? 1 : 0); }
   static constexpr int LOGE0 = bits(0);          // elements per thread (max radix)
   static constexpr int E = 1 << LOGE0;
   static constexpr int N = 1 << LOGN;
   static constexpr int TPL = N / E;              // threads per line
-  static constexpr int ns(int s) { int n = 1; for (int i = 0; i < s; ++i) n <<= bits(i); return n; }
+  __host__ __device__ static constexpr int ns(int s) { int n = 1; for (int i = 0; i < s; ++i) n <<= bits(i); return n; }
   static constexpr int LOGPAD = LOGE0;           // one pad element every E elements
   static constexpr int LD = N + (N >> LOGPAD) + 1;   // padded line length (odd-ish)
   static constexpr int MAXT = (TPL > 512) ? TPL : ((E <= 8) ? 512 : (TPL > 256 ? TPL : 256));
@@ -134,7 +134,7 @@ template <typename T> __device__ __forceinline__ cx<T> fs_twiddle(const TilePara
 }
 
 template <typename T, int LOGN, int LOGE>
-__global__ void __launch_bounds__(Sched<LOGN, LOGE>::MAXT) fft_tile_kernel(const TileParams<T> p) {
+__global__ void __launch_bounds__(Sched<LOGN, LOGE>::MAXT, (Sched<LOGN, LOGE>::MAXT <= 512 ? 2 : 1)) fft_tile_kernel(const TileParams<T> p) {
   typedef Sched<LOGN, LOGE> S;
   typedef cx<T> C;
   JTB_DYN_SMEM(smem_raw);

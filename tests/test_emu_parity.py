@@ -135,3 +135,19 @@ def test_errors(jt):
     a = np.array([3.0, 4.0])
     jt.DoubleFFT_1D(1).complexForward(a)       # n == 1 is a no-op
     assert a.tolist() == [3.0, 4.0]
+
+
+# shapes that dispatch to the lean fft_fast_kernel (jtb_fast.cuh): contiguous and strided layouts
+@pytest.mark.parametrize("prec,dims", [("Double", (512, 16)), ("Double", (64, 64)), ("Double", (1024, 8)),
+                                       ("Double", (8, 2048)), ("Double", (2, 4096)), ("Float", (512, 32)),
+                                       ("Float", (1024, 16)), ("Float", (2048, 8)), ("Double", (8, 16, 512))])
+def test_fast_kernel_shapes(jt, prec, dims):
+    pc.fftnd_complex(jt, prec, dims)
+
+
+def test_fast_kernel_variants(jt, monkeypatch):
+    for ws, wc in ((4, 1), (8, 2), (4, 8)):
+        monkeypatch.setenv("JTB_FAST_WS", str(ws))
+        monkeypatch.setenv("JTB_FAST_WC", str(wc))
+        pc.fftnd_complex(jt, "Double", (512, 8) if ws <= 8 else (512, 16))
+        pc.fft1d_batch(jt, "Double", 512, 3, pad=2)
