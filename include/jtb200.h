@@ -65,6 +65,23 @@ int jtb_exec_device(jtb_plan* plan, int op, void* dev_a, int64_t howmany, int64_
 int jtb_lines_c2c_device(int prec, int device, void* dev_a, int64_t n, int64_t nlines, int64_t c0, int64_t d0,
                          int64_t d3, int64_t stride, int inverse, double scale, void* stream);
 
+/* Slab-decomposed 3-D transform over P GPUs (one process per GPU).  Rank g holds slices [g*Ls, (g+1)*Ls) as
+ * [Ls][R][C].  jtb_fft3d_k2_scatter runs the row-axis (k2) pass of every local slice and stores each output
+ * row straight into the receive buffer of the GPU that owns it after re-slabbing over k2 (peer h = k2/(R/P)
+ * receives [g*Ls+ls][k2 % (R/P)][c] of its [S][R/P][C] block): the all-to-all of the transpose is fused into
+ * the kernel's stores over NVLink peer mappings.  recv_ptrs[h] = peer-mapped pointer of rank h's buffer.
+ * Replaces cdft3db_subth's slice-axis gather (fft/DoubleFFT_3D.java:6318-6520) across devices. */
+int jtb_fft3d_k2_scatter(int prec, int device, const void* local_a, int64_t Ls, int64_t R, int64_t C, int nranks,
+                         int rank, void* const* recv_ptrs, int inverse, void* stream);
+/* device-side barrier between the ranks on `stream`: publishes `epoch` into every peer's flag array and waits
+ * for all peers to publish it (flag_ptrs[h] = peer-mapped int64[nranks] of rank h, zero-initialised). */
+int jtb_peer_barrier(int device, void* const* flag_ptrs, int nranks, int rank, int64_t epoch, void* stream);
+/* peer-shareable device memory: allocate + 64-byte IPC handle; map a peer's handle; unmap; free */
+int jtb_peer_alloc(int device, int64_t bytes, void** dev_ptr, unsigned char* handle64);
+int jtb_peer_open(int device, const unsigned char* handle64, void** peer_ptr);
+int jtb_peer_close(int device, void* peer_ptr);
+int jtb_peer_free(int device, void* dev_ptr);
+
 /* pinned host memory for callers that want DMA-speed jtb_exec (Java: off-heap segments / LargeArray storage) */
 int jtb_host_alloc(void** out, int64_t bytes);
 int jtb_host_free(void* p);

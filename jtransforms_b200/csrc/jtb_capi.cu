@@ -289,6 +289,74 @@ int jtb_lines_c2c_device(int prec, int device, void* dev_a, int64_t n, int64_t n
   return e.c2c_lines((float2*)dev_a, g, nlines, n, inverse != 0, has_scale, (float)scale);
 }
 
+int jtb_fft3d_k2_scatter(int prec, int device, const void* local_a, int64_t Ls, int64_t R, int64_t Cn, int nranks,
+                         int rank, void* const* recv_ptrs, int inverse, void* stream) {
+  if (!local_a || !recv_ptrs || Ls < 1 || R < 2 || Cn < 1 || rank < 0 || rank >= nranks) { set_error("bad argument"); return ST_ARG; }
+  Ctx* c = get_ctx(device);
+  if (!c) return ST_CUDA;
+  std::lock_guard<std::mutex> lk(c->mu);
+  JTB_CUDA(cudaSetDevice(device));
+  if (prec == JTB_F64) {
+    Engine<double> e(c, (cudaStream_t)stream);
+    return fast_scatter<double>(e, (const double2*)local_a, Ls, R, Cn, nranks, rank, recv_ptrs, inverse != 0);
+  }
+  Engine<float> e(c, (cudaStream_t)stream);
+  return fast_scatter<float>(e, (const float2*)local_a, Ls, R, Cn, nranks, rank, recv_ptrs, inverse != 0);
+}
+
+int jtb_peer_barrier(int device, void* const* flag_ptrs, int nranks, int rank, int64_t epoch, void* stream) {
+  Ctx* c = get_ctx(device);
+  if (!c) return ST_CUDA;
+  if (!flag_ptrs || rank < 0 || rank >= nranks) { set_error("bad argument"); return ST_ARG; }
+  JTB_CUDA(cudaSetDevice(device));
+  return peer_barrier(c, (cudaStream_t)stream, flag_ptrs, nranks, rank, (long long)epoch);
+}
+
+int jtb_peer_alloc(int device, int64_t bytes, void** dev_ptr, unsigned char* handle64) {
+  if (!dev_ptr || !handle64 || bytes < 1) { set_error("bad argument"); return ST_ARG; }
+  if (!get_ctx(device)) return ST_CUDA;
+  JTB_CUDA(cudaSetDevice(device));
+  JTB_CUDA(cudaMalloc(dev_ptr, (size_t)bytes));
+  JTB_CUDA(cudaMemset(*dev_ptr, 0, (size_t)bytes));
+  memset(handle64, 0, 64);
+#ifdef JTB_EMU
+  memcpy(handle64, dev_ptr, sizeof(void*));
+#else
+  cudaIpcMemHandle_t h;
+  JTB_CUDA(cudaIpcGetMemHandle(&h, *dev_ptr));
+  static_assert(sizeof(h) == 64, "ipc handle size");
+  memcpy(handle64, &h, 64);
+#endif
+  return ST_OK;
+}
+int jtb_peer_open(int device, const unsigned char* handle64, void** peer_ptr) {
+  if (!handle64 || !peer_ptr) { set_error("bad argument"); return ST_ARG; }
+  if (!get_ctx(device)) return ST_CUDA;
+  JTB_CUDA(cudaSetDevice(device));
+#ifdef JTB_EMU
+  memcpy(peer_ptr, handle64, sizeof(void*));
+#else
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  JTB_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+#endif
+  return ST_OK;
+}
+int jtb_peer_close(int device, void* peer_ptr) {
+  if (!get_ctx(device)) return ST_CUDA;
+#ifndef JTB_EMU
+  JTB_CUDA(cudaSetDevice(device));
+  if (peer_ptr) JTB_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+#endif
+  return ST_OK;
+}
+int jtb_peer_free(int device, void* dev_ptr) {
+  if (!get_ctx(device)) return ST_CUDA;
+  JTB_CUDA(cudaSetDevice(device));
+  if (dev_ptr) JTB_CUDA(cudaFree(dev_ptr));
+  return ST_OK;
+}
+
 int jtb_host_alloc(void** out, int64_t bytes) {
   if (!out || bytes < 0) { set_error("bad argument"); return ST_ARG; }
   if (!get_ctx(0)) return ST_CUDA;

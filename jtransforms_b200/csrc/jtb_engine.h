@@ -99,6 +99,11 @@ template <typename T> struct Engine {
   int r2r_lines(T* a, const Geo& g, i64 nlines, i64 n, int kind, bool inverse, bool scale);
 };
 
+template <typename T>
+int fast_scatter(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, int nranks, int rank, void* const* peers,
+                 bool inverse);   // jtb_fast.cu
+int peer_barrier(Ctx* ctx, cudaStream_t st, void* const* flag_ptrs, int nranks, int rank, long long epoch);
+
 extern template struct Engine<double>;
 extern template struct Engine<float>;
 

@@ -124,6 +124,99 @@ int fast_c2c(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, int logn, bool in
   return ST_OK;
 }
 
+// ------------------------------------------------------------------------------------------ fused k2 + exchange
+namespace {
+template <typename T> struct ScatterEntry {
+  int logn, W, threads, smem, loge;
+  void (*kern)(const ScatterParams<T>);
+  bool attr_done;
+};
+template <typename T, int LOGN, int LOGE, int W> ScatterEntry<T> make_scatter() {
+  typedef Sched<LOGN, LOGE> S;
+  ScatterEntry<T> e;
+  e.logn = LOGN; e.loge = LOGE; e.W = W; e.threads = W * S::TPL;
+  e.smem = (int)((FastAddr<T, S, true, W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
+  e.kern = fft_scatter_kernel<T, LOGN, LOGE, W>;
+  e.attr_done = false;
+  return e;
+}
+template <typename T> std::vector<ScatterEntry<T>>& scatter_registry();
+template <> std::vector<ScatterEntry<double>>& scatter_registry<double>() {
+  static std::vector<ScatterEntry<double>> r = {make_scatter<double, 9, 3, 8>(), make_scatter<double, 6, 3, 8>(),
+                                                make_scatter<double, 10, 4, 8>()};
+  return r;
+}
+template <> std::vector<ScatterEntry<float>>& scatter_registry<float>() {
+  static std::vector<ScatterEntry<float>> r = {make_scatter<float, 9, 3, 16>(), make_scatter<float, 6, 3, 16>()};
+  return r;
+}
+}  // namespace
+
+template <typename T>
+int fast_scatter(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, int nranks, int rank, void* const* peers,
+                 bool inverse) {
+  if (!is_pow2(R) || nranks < 1 || nranks > 8 || !is_pow2(nranks) || R % nranks) {
+    set_error("fused exchange needs power-of-two rows and 1, 2, 4 or 8 ranks");
+    return ST_UNSUPPORTED;
+  }
+  const int logn = ilog2(R);
+  ScatterEntry<T>* pick = nullptr;
+  for (auto& f : scatter_registry<T>())
+    if (f.logn == logn && Cn % f.W == 0) { pick = &f; break; }
+  if (!pick) { set_error("no fused-exchange kernel for %lld rows x %lld columns", (long long)R, (long long)Cn); return ST_UNSUPPORTED; }
+  if (Ls * (Cn / pick->W) > 0x7fffffffLL || Ls * R * Cn >= (1LL << 40)) { set_error("slab too large"); return ST_UNSUPPORTED; }
+  if (!pick->attr_done) {
+    JTB_CUDA(cudaFuncSetAttribute(pick->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pick->smem));
+    pick->attr_done = true;
+  }
+  ScatterParams<T> p;
+  p.a = a;
+  for (int h = 0; h < 8; ++h) p.peer[h] = h < nranks ? (cx<T>*)peers[h] : nullptr;
+  p.Ls = (int)Ls; p.C = (int)Cn; p.logRh = ilog2(R / nranks); p.slice0 = (int)(rank * Ls); p.inverse = inverse;
+  // the table layout only depends on (logn, loge): share it with fast_c2c through a pseudo entry
+  FastEntry<T> fe;
+  fe.logn = logn; fe.loge = pick->loge;
+  {
+    const TileInfo ti = tile_info(logn);
+    (void)ti;
+  }
+  // stage schedule of Sched<logn, loge>
+  {
+    const int Sn = (logn <= pick->loge) ? 1 : (logn + pick->loge - 1) / pick->loge;
+    fe.nstages = Sn;
+    fe.twcount = 0;
+    int ns = 1;
+    for (int s = 0; s < JTB_MAX_STAGES; ++s) {
+      fe.bits[s] = s < Sn ? (logn / Sn + (s < logn % Sn ? 1 : 0)) : 0;
+      if (s > 0 && s < Sn) fe.twcount += fe.bits[s] * ns;
+      ns <<= fe.bits[s];
+    }
+  }
+  JTB_TRY(fast_table(e, fe, &p.twg));
+  const unsigned nblk = (unsigned)(Ls * (Cn / pick->W));
+  JTB_LAUNCH(pick->kern, nblk, (unsigned)pick->threads, (size_t)pick->smem, e.st, p);
+  JTB_CUDA(cudaGetLastError());
+  e.ctx->launches++;
+  return ST_OK;
+}
+
+int peer_barrier(Ctx* ctx, cudaStream_t st, void* const* flag_ptrs, int nranks, int rank, long long epoch) {
+  if (nranks < 1 || nranks > 8) { set_error("1..8 ranks"); return ST_ARG; }
+  PeerFlags pf;
+  for (int h = 0; h < 8; ++h) pf.f[h] = h < nranks ? (long long*)flag_ptrs[h] : nullptr;
+  static int* err = nullptr;
+  if (!err) {
+    JTB_CUDA(cudaMalloc((void**)&err, sizeof(int)));
+    JTB_CUDA(cudaMemset(err, 0, sizeof(int)));
+  }
+  JTB_LAUNCH(peer_barrier_kernel, 1u, 32u, 0, st, pf, nranks, rank, epoch, err);
+  JTB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return ST_OK;
+}
+
+template int fast_scatter<double>(Engine<double>&, const double2*, i64, i64, i64, int, int, void* const*, bool);
+template int fast_scatter<float>(Engine<float>&, const float2*, i64, i64, i64, int, int, void* const*, bool);
 template int fast_c2c<double>(Engine<double>&, double2*, const Geo&, i64, int, bool, bool, double, bool*);
 template int fast_c2c<float>(Engine<float>&, float2*, const Geo&, i64, int, bool, bool, float, bool*);
 

@@ -161,6 +161,84 @@ fft_fast_kernel(const FastParams<T> p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// k2 pass of a slab-decomposed 3-D transform with the re-slabbing all-to-all fused into its stores.
+// Rank g holds slices [g*Ls, (g+1)*Ls) as [Ls][R][C].  The kernel transforms the columns (length R,
+// stride C) of every local slice and stores output row k2 straight into the receive buffer of the GPU
+// that owns it after the exchange: peer h = k2 / Rh gets it at [g*Ls + ls][k2 % Rh][c] of its
+// [S][Rh][C] block.  peer[h] are peer-mapped device pointers (NVLink P2P; peer[g] is local memory).
+// Replaces the slice-axis gather of cdft3db_subth (fft/DoubleFFT_3D.java:6318-6520) across GPUs.
+template <typename T> struct ScatterParams {
+  const cx<T>* a;     // local slab [Ls][R][C]
+  cx<T>* peer[8];     // receive buffers [S][Rh][C], one per rank
+  int Ls, C, logRh;   // local slices, columns, log2(R / nranks)
+  int slice0;         // g * Ls
+  int inverse;
+  const cx<T>* twg;
+};
+
+template <typename T, int LOGN, int LOGE, int W>
+__global__ void __launch_bounds__(W * Sched<LOGN, LOGE>::TPL, (Sched<LOGN, LOGE>::E <= 8 ? FastOcc<W * Sched<LOGN, LOGE>::TPL>::MINB
+                                                                                      : (FastOcc<W * Sched<LOGN, LOGE>::TPL>::MINB + 1) / 2))
+fft_scatter_kernel(const ScatterParams<T> p) {
+  typedef Sched<LOGN, LOGE> S;
+  typedef cx<T> C;
+  typedef FastAddr<T, S, true, W> A;
+  JTB_DYN_SMEM(smem_raw);
+  C* sm = reinterpret_cast<C*>(smem_raw);
+  C* twt = sm + A::TILE;
+  const int tid = threadIdx.x;
+  const int w = tid % W, t = tid / W;
+  for (int i = tid; i < FastTw<S>::COUNT; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
+  const int groups = p.C / W;                       // column groups per slice
+  const int ls = blockIdx.x / groups;
+  const int c = (blockIdx.x - ls * groups) * W + w;
+  const C* src = p.a + (i64)ls * S::N * p.C + c;
+  C v[S::E];
+#pragma unroll
+  for (int q = 0; q < S::E; ++q) v[q] = src[(i64)(t + q * S::TPL) * p.C];
+  if (p.inverse) {
+#pragma unroll
+    for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
+  }
+  FastLoop<T, S, 0, true, W>::run(v, sm, twt, t, w);
+  if (p.inverse) {
+#pragma unroll
+    for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
+  }
+  const int Rh = 1 << p.logRh;
+  const i64 row0 = (i64)(p.slice0 + ls) * Rh;
+#pragma unroll
+  for (int q = 0; q < S::E; ++q) {
+    const int k2 = t + q * S::TPL;
+    const int h = k2 >> p.logRh;
+    const int rl = k2 & (Rh - 1);
+    p.peer[h][(row0 + rl) * p.C + c] = v[q];
+  }
+}
+
+// cross-GPU barrier: thread h publishes `epoch` into rank h's flag array (slot = my rank) and waits until
+// rank h has published it into mine.  flags are peer-mapped int64[nranks] arrays, monotonically increasing.
+struct PeerFlags { long long* f[8]; };
+__global__ void peer_barrier_kernel(const PeerFlags flags, int nranks, int rank, long long epoch, int* err) {
+#ifndef JTB_EMU
+  const int h = threadIdx.x;
+  if (h >= nranks) return;
+  __threadfence_system();
+  volatile long long* theirs = flags.f[h] + rank;
+  *theirs = epoch;
+  __threadfence_system();
+  volatile long long* mine = flags.f[rank] + h;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (*mine < epoch) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 10000000000ULL) { *err = 1; break; }   // 10 s: a peer died; give up instead of hanging the GPU
+  }
+  __threadfence_system();
+#endif
+}
+
 // host-side description of one instantiation
 struct FastInfo {
   int logn, loge, strided, W, threads, smem_bytes, tw_count;

@@ -4,7 +4,13 @@ Replaces the shared-memory slice-axis gather of the reference (cdft3db_subth,
 fft/DoubleFFT_3D.java:6318-6520) when one transform is spread over P GPUs:
 
   rank g owns slices [g*S/P, (g+1)*S/P)  ->  local k3 and k2 passes (fft/DoubleFFT_3D.java:5505-5713)
-  -> all-to-all re-slabbing over k2 (NCCL over NVLink)  ->  k1 pass on [S][R/P][C]
+  -> all-to-all re-slabbing over k2  ->  k1 pass on [S][R/P][C]
+
+Two exchange implementations:
+  * "p2p"  (default on GPUs): the k2 kernel itself stores every output row into the receive buffer of the GPU
+    that owns it (peer-mapped memory over NVLink/NVSwitch, jtb_fft3d_k2_scatter), followed by a device-side
+    flag barrier -- the transpose costs no extra pass over HBM and no pack/unpack.
+  * "nccl": k2 in place, pack, torch.distributed.all_to_all_single, then k1 (baseline; also the gloo CPU path).
 
 The result is left k2-slabbed: rank h holds out[k1][h*R/P:(h+1)*R/P][k3] as a contiguous [S][R/P][C] block,
 which ``scatter_to_host`` places into the caller's natural-order host array with strided copies.
@@ -20,7 +26,8 @@ from . import _lib
 
 
 class SlabFFT3D:
-    def __init__(self, slices: int, rows: int, columns: int, prec: int = _lib.F64, group=None, device_index=None):
+    def __init__(self, slices: int, rows: int, columns: int, prec: int = _lib.F64, group=None, device_index=None,
+                 exchange: str = "auto"):
         self.S, self.R, self.Cn, self.prec, self.group = int(slices), int(rows), int(columns), prec, group
         self.P = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -30,6 +37,63 @@ class SlabFFT3D:
         self.dtype = torch.float64 if prec == _lib.F64 else torch.float32
         self.dev = 0 if device_index is None else int(device_index)
         self.lib = _lib.get()
+        self.esize = 8 if prec == _lib.F64 else 4
+        if exchange == "auto":
+            exchange = "p2p" if (self.P > 1 and dist.is_initialized() and dist.get_backend(group) == "nccl") else "nccl"
+        self.exchange = exchange
+        self.step = 0
+        self._peer = None
+        if self.P > 1 and exchange == "p2p":
+            self._setup_p2p()
+
+    # ---- peer-mapped receive buffers (double buffered) + barrier flags
+    def _setup_p2p(self):
+        lib, P = self.lib, self.P
+        nbytes = 2 * self.S * self.Rh * self.Cn * self.esize
+        mine, handles = [], []
+        for size in (nbytes, nbytes, 4096):
+            ptr, h = C.c_void_p(), C.create_string_buffer(64)
+            _lib.check(lib.jtb_peer_alloc(self.dev, size, C.byref(ptr), h))
+            mine.append(ptr.value)
+            handles.append(bytes(h.raw))
+        allh = [None] * P
+        dist.all_gather_object(allh, handles, group=self.group)
+        ptrs = [[0] * P for _ in range(3)]
+        for r in range(P):
+            for b in range(3):
+                if r == self.rank:
+                    ptrs[b][r] = mine[b]
+                else:
+                    q = C.c_void_p()
+                    _lib.check(lib.jtb_peer_open(self.dev, allh[r][b], C.byref(q)))
+                    ptrs[b][r] = q.value
+        self._peer = {"mine": mine, "ptrs": ptrs, "nbytes": nbytes,
+                      "arr": [(C.c_void_p * P)(*ptrs[b]) for b in range(3)]}
+        dist.barrier(group=self.group)
+
+    def _recv_tensor(self, b: int) -> torch.Tensor:
+        class _Wrap:
+            pass
+        wobj = _Wrap()
+        wobj.__cuda_array_interface__ = {
+            "shape": (2 * self.S * self.Rh * self.Cn,), "typestr": "<f8" if self.esize == 8 else "<f4",
+            "data": (self._peer["mine"][b], False), "version": 3}
+        return torch.as_tensor(wobj, device=torch.device("cuda", self.dev))
+
+    def close(self):
+        if self._peer:
+            torch.cuda.synchronize()
+            if dist.is_initialized():
+                dist.barrier(group=self.group)
+            for b in range(3):
+                for r in range(self.P):
+                    if r != self.rank:
+                        self.lib.jtb_peer_close(self.dev, C.c_void_p(self._peer["ptrs"][b][r]))
+            if dist.is_initialized():
+                dist.barrier(group=self.group)
+            for m in self._peer["mine"]:
+                self.lib.jtb_peer_free(self.dev, C.c_void_p(m))
+            self._peer = None
 
     # number of real elements (doubles/floats) of the local slab, before and after
     def local_elements(self) -> int:
@@ -45,6 +109,17 @@ class SlabFFT3D:
         Returns the tensor holding the k2-slabbed result [S][Rh][C] (``a`` itself when P == 1)."""
         S, R, Cn, P, Ls, Rh = self.S, self.R, self.Cn, self.P, self.Ls, self.Rh
         self._lines(a, Cn, Ls * R, 1, 0, Cn, 1)                       # k3: contiguous rows
+        if P > 1 and self.exchange == "p2p":
+            # fused: k2 pass whose stores ARE the all-to-all (NVLink peer stores), then a device-side barrier
+            b = self.step & 1
+            self.step += 1
+            stream = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
+            _lib.check(self.lib.jtb_fft3d_k2_scatter(self.prec, self.dev, C.c_void_p(a.data_ptr()), Ls, R, Cn, P,
+                                                     self.rank, self._peer["arr"][b], 0, stream))
+            _lib.check(self.lib.jtb_peer_barrier(self.dev, self._peer["arr"][2], P, self.rank, self.step, stream))
+            recv = self._recv_tensor(b)
+            self._lines(recv, S, Rh * Cn, Rh * Cn, 1, S * Rh * Cn, Rh * Cn)
+            return recv
         self._lines(a, R, Cn * Ls, Cn, 1, R * Cn, Cn)                 # k2: columns inside each slice
         if P == 1:
             self._lines(a, S, R * Cn, R * Cn, 1, S * R * Cn, R * Cn)  # k1: across slices

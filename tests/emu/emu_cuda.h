@@ -46,6 +46,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
 #define blockIdx (jtb_emu::t_blockIdx)
 #define blockDim (jtb_emu::t_blockDim)
 #define gridDim (jtb_emu::t_gridDim)
+static inline void __threadfence_system() {}
 static inline void __syncthreads() { pthread_barrier_wait(jtb_emu::g_bar); }
 #define JTB_DYN_SMEM(name) unsigned char* name = jtb_emu::g_smem
 #define JTB_LAUNCH(kern, grid, block, smem, stream, ...) \
@@ -68,6 +69,7 @@ static inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return c
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = 0) { memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }

@@ -177,3 +177,35 @@ def r2r(jt, prec, kind, dims):
         t.forward(a, True)
     t.inverse(a, True)
     check(a, x64, prec, total, "%s round trip %s" % (kind, dims))
+
+
+# ------------------------------------------------------------------ fused k2 + exchange (virtual ranks)
+def slab_scatter_virtual(lib, prec, dims, P, torch_device="cpu", dev_index=0):
+    """Runs the slab-decomposed forward transform with P *virtual* ranks inside one process: every rank's
+    k3 pass and fused k2-scatter (jtb_fft3d_k2_scatter) write into P receive buffers that live on the same
+    device, then each rank's k1 pass runs on its buffer.  Checks the kernel's addressing against the oracle."""
+    import ctypes as C
+    import torch
+    S, R, Cn = dims
+    Ls, Rh = S // P, R // P
+    dt = dtype_of(prec)
+    tdt = torch.float64 if prec == "Double" else torch.float32
+    pcode = 0 if prec == "Double" else 1
+    x = rnd(2 * S * R * Cn, lo=0.0, hi=1.0).astype(dt)
+    locs = [torch.from_numpy(x.reshape(S, -1)[g * Ls:(g + 1) * Ls].copy().ravel()).to(torch_device) for g in range(P)]
+    recvs = [torch.zeros(2 * S * Rh * Cn, dtype=tdt, device=torch_device) for _ in range(P)]
+    arr = (C.c_void_p * P)(*[r.data_ptr() for r in recvs])
+
+    def st():
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream) if torch_device != "cpu" else None
+    for g in range(P):
+        assert lib.jtb_lines_c2c_device(pcode, dev_index, C.c_void_p(locs[g].data_ptr()), Cn, Ls * R, 1, 0, Cn, 1, 0,
+                                        1.0, st()) == 0
+        rc = lib.jtb_fft3d_k2_scatter(pcode, dev_index, C.c_void_p(locs[g].data_ptr()), Ls, R, Cn, P, g, arr, 0, st())
+        assert rc == 0, lib.jtb_last_error()
+    want = o.complex_forward_3d(x.astype(np.float64), S, R, Cn).reshape(S, R, 2 * Cn)
+    for h in range(P):
+        assert lib.jtb_lines_c2c_device(pcode, dev_index, C.c_void_p(recvs[h].data_ptr()), S, Rh * Cn, Rh * Cn, 1,
+                                        S * Rh * Cn, Rh * Cn, 0, 1.0, st()) == 0
+        got = recvs[h].cpu().numpy().reshape(S, Rh, 2 * Cn)
+        check(got, want[:, h * Rh:(h + 1) * Rh], prec, S * R * Cn, "slab scatter P=%d rank %d" % (P, h))

@@ -151,3 +151,14 @@ def test_fast_kernel_variants(jt, monkeypatch):
         monkeypatch.setenv("JTB_FAST_WC", str(wc))
         pc.fftnd_complex(jt, "Double", (512, 8) if ws <= 8 else (512, 16))
         pc.fft1d_batch(jt, "Double", 512, 3, pad=2)
+
+
+@pytest.mark.parametrize("P", [1, 2, 4, 8])
+def test_slab_scatter_virtual_ranks(jt, P):
+    from jtransforms_b200 import _lib
+    pc.slab_scatter_virtual(_lib.get(), "Double", (8, 64, 16), P)
+
+
+def test_slab_scatter_float(jt):
+    from jtransforms_b200 import _lib
+    pc.slab_scatter_virtual(_lib.get(), "Float", (4, 64, 32), 2)
