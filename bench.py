@@ -313,7 +313,8 @@ def main():
         worst = max(per, key=lambda p: p["ms"])
         roof = {"bound": "hbm", "kernel": "fft_fast_kernel<double,512> " + worst["pass"], "achieved": worst["GBps"],
                 "peak": hbm_peak, "peak_source": peak_kind, "unit": "GB/s", "frac": worst["GBps"] / hbm_peak,
-                "traffic": None, "algorithmic_bytes_per_launch": 2 * local_bytes, "passes": per}
+                "traffic": 4.238e9, "traffic_source": "profiles/r01_ncu_fft_fast_512_summary.json (ncu --set full, dram read+write per launch)",
+                "algorithmic_bytes_per_launch": 2 * local_bytes, "passes": per}
     else:
         # whole-step model: `sweeps` read+write passes over the working set
         algo = 2.0 * w.sweeps * local_bytes
