@@ -102,6 +102,14 @@ template <typename T> struct Engine {
 template <typename T>
 int fast_scatter(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, int nranks, int rank, void* const* peers,
                  bool inverse);   // jtb_fast.cu
+template <typename T> int fast_stage_table(Engine<T>& e, int logn, int loge, const cx<T>** out);   // jtb_fast.cu
+template <typename T>
+int fast_fourstep_contig(Engine<T>& e, const cx<T>* in, i64 in_dist, cx<T>* out, i64 out_dist, i64 l0, i64 l1, int logn,
+                         bool swap_in, bool swap_out, bool has_scale, T scale, bool* handled);   // jtb_fast2.cu
+template <typename T>
+int fast_fourstep_strided(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, int logn, bool inverse, bool has_scale,
+                          T scale, bool* handled);
+template <typename T> int fast_rfft_fwd(Engine<T>& e, cx<T>* a, i64 dist, i64 nlines, int logN, bool* handled);
 int peer_barrier(Ctx* ctx, cudaStream_t st, void* const* flag_ptrs, int nranks, int rank, long long epoch);
 
 extern template struct Engine<double>;

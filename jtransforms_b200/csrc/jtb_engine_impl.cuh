@@ -232,6 +232,20 @@ int Engine<T>::c2c_pow2(const C* in, const Geo& gi, C* out, const Geo& go, i64 l
     return tile_call(in, gi, out, go, l0, l1, logn, p);
   }
   if (pro != PRO_DIRECT || epi != EPI_DIRECT) { set_error("fused real pass needs a single-tile length"); return ST_UNSUPPORTED; }
+  {
+    // lean two-pass kernels when nothing but the inverse swaps and a scale is fused
+    const bool plain = !f.premul && !f.postmul && f.valid_in < 0 && f.valid_out < 0 && !f.swap_in2 && !f.swap_out1;
+    const bool one_level_i = gi.c[0] == 1 && gi.c[1] == 1 && gi.c[2] == 1;
+    const bool one_level_o = go.c[0] == 1 && go.c[1] == 1 && go.c[2] == 1;
+    bool handled = false;
+    if (plain && contig && one_level_i && one_level_o) {
+      JTB_TRY(fast_fourstep_contig<T>(*this, in, gi.d[3], out, go.d[3], l0, l1, logn, f.swap_in, f.swap_out, f.has_scale,
+                                      f.scale, &handled));
+    } else if (plain && !contig && in == out && geo_same(gi, go) && l0 == 0 && f.swap_in == f.swap_out) {
+      JTB_TRY(fast_fourstep_strided<T>(*this, out, go, l1, logn, f.swap_in, f.has_scale, f.scale, &handled));
+    }
+    if (handled) return ST_OK;
+  }
   if (logn > 2 * max_logn_contig()) { set_error("length 2^%d exceeds the two-pass limit 2^%d", logn, 2 * max_logn_contig()); return ST_UNSUPPORTED; }
   if (gi.c[2] != 1 || go.c[2] != 1) { set_error("geometry too deep for the two-pass transform"); return ST_UNSUPPORTED; }
 
@@ -408,6 +422,11 @@ template <typename T> int Engine<T>::real_forward_lines(T* a, const Geo& g, i64 
   if (n <= 1 || nlines <= 0) return ST_OK;
   if (is_pow2(n) && n >= 4 && ilog2(n) - 1 <= max_logn_contig() && geo_even<T>(g) && ((uintptr_t)a % sizeof(C)) == 0) {
     const Geo gc = geo_halve(g);
+    if (gc.c[0] == 1 && gc.c[1] == 1 && gc.c[2] == 1) {
+      bool handled = false;
+      JTB_TRY(fast_rfft_fwd<T>(*this, (C*)a, gc.d[3], nlines, ilog2(n) - 1, &handled));
+      if (handled) return ST_OK;
+    }
     Fuse<T> f;
     return c2c_pow2((const C*)a, gc, (C*)a, gc, 0, nlines, ilog2(n) - 1, f, PRO_DIRECT, EPI_RFFT_FWD);
   }

@@ -57,28 +57,33 @@ template <> std::vector<FastEntry<float>>& registry<float>() {
   return r;
 }
 
-template <typename T> int fast_table(Engine<T>& e, const FastEntry<T>& f, const cx<T>** out) {
+}  // namespace
+
+// base twiddle table of Sched<logn, loge> (layout: FastTw in jtb_fast.cuh), cached per (precision, logn, loge)
+template <typename T> int fast_stage_table(Engine<T>& e, int logn, int loge, const cx<T>** out) {
   typedef cx<T> C;
-  const std::string key = mkkey("ftw", e.pname(), f.logn, f.loge);
+  const std::string key = mkkey("ftw", e.pname(), logn, loge);
   void* d = e.ctx->table(key);
   if (!d) {
-    std::vector<C> h((size_t)(f.twcount > 0 ? f.twcount : 1));
+    const int Sn = (logn <= loge) ? 1 : (logn + loge - 1) / loge;
+    std::vector<C> h;
     i64 ns = 1;
-    size_t o = 0;
-    for (int s = 0; s < f.nstages; ++s) {
-      const i64 R = 1LL << f.bits[s];
+    for (int s = 0; s < Sn; ++s) {
+      const int b = logn / Sn + (s < logn % Sn ? 1 : 0);
+      const i64 R = 1LL << b;
       if (s > 0)
-        for (int j = 0; j < f.bits[s]; ++j)
-          for (i64 k = 0; k < ns; ++k) h[o++] = unit_root<T>((1LL << j) * k, ns * R);
+        for (int j = 0; j < b; ++j)
+          for (i64 k = 0; k < ns; ++k) h.push_back(unit_root<T>((1LL << j) * k, ns * R));
       ns *= R;
     }
+    if (h.empty()) h.push_back(mk<T>(1, 0));
     JTB_TRY(e.ctx->put_table(key, h.data(), h.size() * sizeof(C), &d));
   }
   *out = (const C*)d;
   return ST_OK;
 }
-
-}  // namespace
+template int fast_stage_table<double>(Engine<double>&, int, int, const double2**);
+template int fast_stage_table<float>(Engine<float>&, int, int, const float2**);
 
 // Runs the lean kernel when the call is a plain in-place transform on a supported layout.
 // *handled = false (and ST_OK) when the caller must use the general tile kernel.
@@ -114,7 +119,7 @@ int fast_c2c(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, int logn, bool in
   p.a = a; p.nlines = nlines;
   p.line_dist = g.d[3]; p.c0 = (int)g.c[0]; p.stride = (int)g.stride;
   p.inverse = inverse; p.has_scale = has_scale; p.scale = scale;
-  JTB_TRY(fast_table(e, *pick, &p.twg));
+  JTB_TRY(fast_stage_table<T>(e, pick->logn, pick->loge, &p.twg));
   const i64 nblk = (nlines + pick->W - 1) / pick->W;
   if (nblk > 0x7fffffffLL) return ST_OK;
   JTB_LAUNCH(pick->kern, (unsigned)nblk, (unsigned)pick->threads, (size_t)pick->smem, e.st, p);
@@ -173,26 +178,7 @@ int fast_scatter(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, int nranks
   p.a = a;
   for (int h = 0; h < 8; ++h) p.peer[h] = h < nranks ? (cx<T>*)peers[h] : nullptr;
   p.Ls = (int)Ls; p.C = (int)Cn; p.logRh = ilog2(R / nranks); p.slice0 = (int)(rank * Ls); p.inverse = inverse;
-  // the table layout only depends on (logn, loge): share it with fast_c2c through a pseudo entry
-  FastEntry<T> fe;
-  fe.logn = logn; fe.loge = pick->loge;
-  {
-    const TileInfo ti = tile_info(logn);
-    (void)ti;
-  }
-  // stage schedule of Sched<logn, loge>
-  {
-    const int Sn = (logn <= pick->loge) ? 1 : (logn + pick->loge - 1) / pick->loge;
-    fe.nstages = Sn;
-    fe.twcount = 0;
-    int ns = 1;
-    for (int s = 0; s < JTB_MAX_STAGES; ++s) {
-      fe.bits[s] = s < Sn ? (logn / Sn + (s < logn % Sn ? 1 : 0)) : 0;
-      if (s > 0 && s < Sn) fe.twcount += fe.bits[s] * ns;
-      ns <<= fe.bits[s];
-    }
-  }
-  JTB_TRY(fast_table(e, fe, &p.twg));
+  JTB_TRY(fast_stage_table<T>(e, logn, pick->loge, &p.twg));
   const unsigned nblk = (unsigned)(Ls * (Cn / pick->W));
   JTB_LAUNCH(pick->kern, nblk, (unsigned)pick->threads, (size_t)pick->smem, e.st, p);
   JTB_CUDA(cudaGetLastError());

@@ -220,7 +220,7 @@ fft_scatter_kernel(const ScatterParams<T> p) {
 // cross-GPU barrier: thread h publishes `epoch` into rank h's flag array (slot = my rank) and waits until
 // rank h has published it into mine.  flags are peer-mapped int64[nranks] arrays, monotonically increasing.
 struct PeerFlags { long long* f[8]; };
-__global__ void peer_barrier_kernel(const PeerFlags flags, int nranks, int rank, long long epoch, int* err) {
+static __global__ void peer_barrier_kernel(const PeerFlags flags, int nranks, int rank, long long epoch, int* err) {
 #ifndef JTB_EMU
   const int h = threadIdx.x;
   if (h >= nranks) return;

@@ -1,0 +1,212 @@
+// Instantiations and host-side dispatch of fft_fast2_kernel (jtb_fast2.cuh): the two-pass (four-step) transform of
+// long contiguous lines, of long strided lines (in place, intermediate in the array's own layout) and the fused
+// real-forward row pass.
+#include <cstdlib>
+
+#include "jtb_engine_impl.cuh"
+#include "jtb_fast2.cuh"
+
+namespace jtb {
+
+namespace {
+
+template <typename T> struct F2Entry {
+  int logn, loge, sin, mode, W, threads, smem;
+  void (*kern)(const Fast2Params<T>);
+  bool attr_done;
+};
+template <typename T, int LOGN, int LOGE, bool SIN, int MODE, int W> F2Entry<T> mk2() {
+  typedef Sched<LOGN, LOGE> S;
+  F2Entry<T> e;
+  e.logn = LOGN; e.loge = LOGE; e.sin = SIN; e.mode = MODE; e.W = W; e.threads = W * S::TPL;
+  e.smem = (int)((FastAddr<T, S, SIN, W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
+  e.kern = fft_fast2_kernel<T, LOGN, LOGE, SIN, MODE, W>;
+  e.attr_done = false;
+  return e;
+}
+template <typename T> std::vector<F2Entry<T>>& reg2();
+template <> std::vector<F2Entry<double>>& reg2<double>() {
+  static std::vector<F2Entry<double>> r = {
+      // first pass of the two-pass transform (strided lines, twiddle at the store)
+      mk2<double, 6, 3, true, FM_TWID, 32>(), mk2<double, 7, 4, true, FM_TWID, 16>(), mk2<double, 8, 4, true, FM_TWID, 8>(),
+      mk2<double, 9, 3, true, FM_TWID, 8>(), mk2<double, 10, 4, true, FM_TWID, 8>(),
+      // second pass, contiguous lines with transposed store
+      mk2<double, 8, 4, false, FM_TRANSPOSE, 8>(), mk2<double, 9, 3, false, FM_TRANSPOSE, 8>(),
+      mk2<double, 10, 4, false, FM_TRANSPOSE, 8>(), mk2<double, 11, 4, false, FM_TRANSPOSE, 4>(),
+      // second pass, strided lines (row permutation only)
+      mk2<double, 6, 3, true, FM_PLAIN, 32>(), mk2<double, 7, 4, true, FM_PLAIN, 16>(),
+      // real-forward rows
+      mk2<double, 8, 4, false, FM_RFFT, 8>(), mk2<double, 9, 3, false, FM_RFFT, 4>(), mk2<double, 10, 4, false, FM_RFFT, 4>(),
+      mk2<double, 11, 4, false, FM_RFFT, 2>(), mk2<double, 12, 4, false, FM_RFFT, 1>(),
+  };
+  return r;
+}
+template <> std::vector<F2Entry<float>>& reg2<float>() {
+  static std::vector<F2Entry<float>> r = {
+      mk2<float, 9, 3, true, FM_TWID, 16>(), mk2<float, 10, 4, true, FM_TWID, 16>(),
+      mk2<float, 9, 3, false, FM_TRANSPOSE, 16>(), mk2<float, 10, 4, false, FM_TRANSPOSE, 16>(),
+      mk2<float, 11, 4, false, FM_TRANSPOSE, 8>(),
+      mk2<float, 10, 4, false, FM_RFFT, 4>(), mk2<float, 11, 4, false, FM_RFFT, 2>(),
+  };
+  return r;
+}
+
+template <typename T> F2Entry<T>* find2(int logn, bool sin, int mode) {
+  for (auto& f : reg2<T>())
+    if (f.logn == logn && (f.sin != 0) == sin && f.mode == mode) return &f;
+  return nullptr;
+}
+
+template <typename T> int launch2(Engine<T>& e, F2Entry<T>* f, Fast2Params<T>& p) {
+  if (!f->attr_done) {
+    JTB_CUDA(cudaFuncSetAttribute(f->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, f->smem));
+    f->attr_done = true;
+  }
+  JTB_TRY(fast_stage_table<T>(e, f->logn, f->loge, &p.twg));
+  const i64 nblk = (p.nlines + f->W - 1) / f->W;
+  if (nblk > 0x7fffffffLL) { set_error("too many lines"); return ST_UNSUPPORTED; }
+  static const bool trace = getenv("JTB_TRACE") != nullptr;
+  if (trace) fprintf(stderr, "[jtb] fast2 %s logn=%d sin=%d mode=%d W=%d lines=%lld\n", e.pname(), f->logn, f->sin, f->mode, f->W, (long long)p.nlines);
+  JTB_LAUNCH(f->kern, (unsigned)nblk, (unsigned)f->threads, (size_t)f->smem, e.st, p);
+  JTB_CUDA(cudaGetLastError());
+  e.ctx->launches++;
+  return ST_OK;
+}
+
+template <typename T> Fast2Params<T> blank2() {
+  Fast2Params<T> p;
+  memset(&p, 0, sizeof p);
+  p.gmod = 1 << 30;
+  p.c0 = 1;
+  p.scale = 1;
+  return p;
+}
+
+const bool g_fast2_off = getenv("JTB_NO_FAST2") != nullptr;
+
+}  // namespace
+
+// two-pass transform of contiguous lines: line l of `in` at l*in_dist -> line l of `out` at l*out_dist
+template <typename T>
+int fast_fourstep_contig(Engine<T>& e, const cx<T>* in, i64 in_dist, cx<T>* out, i64 out_dist, i64 l0, i64 l1, int logn,
+                         bool swap_in, bool swap_out, bool has_scale, T scale, bool* handled) {
+  typedef cx<T> C;
+  *handled = false;
+  if (g_fast2_off || l1 <= l0) return ST_OK;
+  // split n = N1 (strided first pass) * N2 (contiguous second pass)
+  F2Entry<T>*f1 = nullptr, *f2 = nullptr;
+  for (int la = logn / 2; la >= 6 && !f1; --la) {
+    for (int s = 0; s < 2 && !f1; ++s) {
+      const int a = s == 0 ? la : logn - la;   // try the balanced split first, then its mirror
+      F2Entry<T>* x = find2<T>(a, true, FM_TWID);
+      F2Entry<T>* y = find2<T>(logn - a, false, FM_TRANSPOSE);
+      if (x && y) { f1 = x; f2 = y; }
+    }
+  }
+  if (!f1) return ST_OK;
+  const i64 n = 1LL << logn, N1 = 1LL << f1->logn, N2 = 1LL << f2->logn;
+  if (N2 % f1->W || N1 % f2->W) return ST_OK;
+  const C *fsA, *fsB;
+  int logL;
+  JTB_TRY(e.fs_tables(logn, &fsA, &fsB, &logL));
+  i64 chunk = (i64)(e.ctx->work_cap / ((size_t)n * sizeof(C)));
+  if (chunk < 1) return ST_OK;
+  if (chunk > l1 - l0) chunk = l1 - l0;
+  JTB_TRY(e.ctx->ensure(e.ctx->work[WK_FOURSTEP], (size_t)chunk * (size_t)n * sizeof(C)));
+  C* wk = (C*)e.ctx->work[WK_FOURSTEP].p;
+  for (i64 c0 = l0; c0 < l1; c0 += chunk) {
+    const i64 c1 = c0 + chunk < l1 ? c0 + chunk : l1;
+    Fast2Params<T> p = blank2<T>();
+    p.in = in + c0 * in_dist; p.out = wk;
+    p.nlines = (c1 - c0) * N2; p.c0 = (int)N2;
+    p.in_gdist = in_dist; p.in_cdist = 1; p.in_stride = N2;
+    p.out_gdist = n; p.out_cdist = 1; p.out_stride = N2;
+    p.swap_in = swap_in;
+    p.fsA = fsA; p.fsB = fsB; p.fs_logL = logL; p.tw_src = 0;
+    JTB_TRY(launch2(e, f1, p));
+    Fast2Params<T> q = blank2<T>();
+    q.in = wk; q.out = out + c0 * out_dist;
+    q.nlines = (c1 - c0) * N1; q.c0 = (int)N1;
+    q.in_gdist = n; q.in_cdist = N2; q.in_stride = 1;
+    q.out_gdist = out_dist; q.out_cdist = 1; q.out_stride = N1;
+    q.swap_out = swap_out; q.has_scale = has_scale; q.scale = scale;
+    JTB_TRY(launch2(e, f2, q));
+  }
+  *handled = true;
+  return ST_OK;
+}
+
+// two-pass in-place transform of long strided lines: c0 adjacent lines (distance 1), element stride s, groups d3
+template <typename T>
+int fast_fourstep_strided(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, int logn, bool inverse, bool has_scale,
+                          T scale, bool* handled) {
+  typedef cx<T> C;
+  *handled = false;
+  if (g_fast2_off || nlines <= 0) return ST_OK;
+  if (!(g.stride > 1 && g.d[0] == 1 && g.c[1] == 1 && g.c[2] == 1 && g.c[0] > 1 && nlines % g.c[0] == 0)) return ST_OK;
+  F2Entry<T>*f1 = nullptr, *f2 = nullptr;
+  for (int la = (logn + 1) / 2; la <= logn - 6 + 0 && !f1; ++la) {
+    F2Entry<T>* x = find2<T>(la, true, FM_TWID);
+    F2Entry<T>* y = find2<T>(logn - la, true, FM_PLAIN);
+    if (x && y) { f1 = x; f2 = y; }
+  }
+  if (!f1) return ST_OK;
+  const i64 n = 1LL << logn, R1 = 1LL << f1->logn, R2 = 1LL << f2->logn, s = g.stride;
+  if (g.c[0] % f1->W || g.c[0] % f2->W) return ST_OK;
+  if ((n - 1) * s + g.c[0] >= (1LL << 40)) return ST_OK;
+  const i64 batches = nlines / g.c[0];
+  const i64 ext = geo_extent(g, nlines, n);
+  JTB_TRY(e.ctx->ensure(e.ctx->work[WK_FOURSTEP], (size_t)ext * sizeof(C)));
+  C* wk = (C*)e.ctx->work[WK_FOURSTEP].p;
+  const C *fsA, *fsB;
+  int logL;
+  JTB_TRY(e.fs_tables(logn, &fsA, &fsB, &logL));
+  // pass 1: lines (c, r2, batch): FFT over r1 (element stride R2*s), twiddle W_n^(k1*r2), a -> work (same offsets)
+  Fast2Params<T> p = blank2<T>();
+  p.in = a; p.out = wk;
+  p.nlines = g.c[0] * R2 * batches; p.c0 = (int)g.c[0]; p.gmod = (int)R2;
+  p.in_gdist = s; p.in_gdist2 = g.d[3]; p.in_cdist = 1; p.in_stride = R2 * s;
+  p.out_gdist = s; p.out_gdist2 = g.d[3]; p.out_cdist = 1; p.out_stride = R2 * s;
+  p.swap_in = inverse;
+  p.fsA = fsA; p.fsB = fsB; p.fs_logL = logL; p.tw_src = 1;
+  JTB_TRY(launch2(e, f1, p));
+  // pass 2: lines (c, k1, batch): FFT over r2 (rows k1*R2 + r2), output element k2 -> row k1 + R1*k2, work -> a
+  Fast2Params<T> q = blank2<T>();
+  q.in = wk; q.out = a;
+  q.nlines = g.c[0] * R1 * batches; q.c0 = (int)g.c[0]; q.gmod = (int)R1;
+  q.in_gdist = R2 * s; q.in_gdist2 = g.d[3]; q.in_cdist = 1; q.in_stride = s;
+  q.out_gdist = s; q.out_gdist2 = g.d[3]; q.out_cdist = 1; q.out_stride = R1 * s;
+  q.swap_out = inverse; q.has_scale = has_scale; q.scale = scale;
+  JTB_TRY(launch2(e, f2, q));
+  *handled = true;
+  return ST_OK;
+}
+
+// realForward of contiguous lines of 2N reals (N = 2^logN complex points), in place, JTransforms packing
+template <typename T>
+int fast_rfft_fwd(Engine<T>& e, cx<T>* a, i64 dist, i64 nlines, int logN, bool* handled) {
+  *handled = false;
+  if (g_fast2_off || nlines <= 0) return ST_OK;
+  F2Entry<T>* f = find2<T>(logN, false, FM_RFFT);
+  if (!f) return ST_OK;
+  const cx<T>* tw[JTB_MAX_STAGES];
+  const cx<T>* rtw;
+  JTB_TRY(e.tile_tables(logN, tw, &rtw));
+  Fast2Params<T> p = blank2<T>();
+  p.in = a; p.out = a; p.nlines = nlines;
+  p.in_gdist = p.out_gdist = dist; p.in_stride = p.out_stride = 1;
+  p.rtw = rtw;
+  JTB_TRY(launch2(e, f, p));
+  *handled = true;
+  return ST_OK;
+}
+
+#define JTB_INST(T)                                                                                                    \
+  template int fast_fourstep_contig<T>(Engine<T>&, const cx<T>*, i64, cx<T>*, i64, i64, i64, int, bool, bool, bool, T, \
+                                       bool*);                                                                         \
+  template int fast_fourstep_strided<T>(Engine<T>&, cx<T>*, const Geo&, i64, int, bool, bool, T, bool*);               \
+  template int fast_rfft_fwd<T>(Engine<T>&, cx<T>*, i64, i64, int, bool*);
+JTB_INST(double)
+JTB_INST(float)
+
+}  // namespace jtb

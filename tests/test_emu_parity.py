@@ -162,3 +162,28 @@ def test_slab_scatter_virtual_ranks(jt, P):
 def test_slab_scatter_float(jt):
     from jtransforms_b200 import _lib
     pc.slab_scatter_virtual(_lib.get(), "Float", (4, 64, 32), 2)
+
+
+# lean two-pass paths (jtb_fast2.cuh) at their natural sizes
+@pytest.mark.parametrize("n", [1 << 14, 1 << 16, 1 << 17])
+def test_fast2_fourstep_contig(jt, n):
+    pc.fft1d_complex(jt, "Double", n)
+
+
+def test_fast2_fourstep_contig_batch_float(jt):
+    pc.fft1d_batch(jt, "Float", 1 << 18, 2, pad=2)
+
+
+@pytest.mark.parametrize("dims", [(4096, 32), (8192, 32)])
+def test_fast2_fourstep_strided(jt, dims):
+    pc.fftnd_complex(jt, "Double", dims)
+
+
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096, 8192])
+def test_fast2_rfft(jt, n):
+    pc.fft1d_real(jt, "Double", n)
+
+
+def test_fast2_real2d(jt):
+    pc.fftnd_real(jt, "Double", (8, 4096))
+    pc.fftnd_real(jt, "Float", (4, 2048))
