@@ -85,6 +85,9 @@ template <typename T> int Engine<T>::tile_tables(int logn, const C** tw, const C
 
 template <typename T> int Engine<T>::fs_tables(int logN, const C** A, const C** B, int* logL) {
   const int lL = logN / 2;
+  // hot-path cache in front of the string-keyed table map
+  static thread_local struct { const void* ctx; int logn; const C* a; const C* b; } memo = {nullptr, 0, nullptr, nullptr};
+  if (memo.ctx == (const void*)ctx && memo.logn == logN) { *A = memo.a; *B = memo.b; *logL = lL; return ST_OK; }
   const i64 N = 1LL << logN, L = 1LL << lL, H = N >> lL;
   const std::string ka = mkkey("fsA", pname(), logN), kb = mkkey("fsB", pname(), logN);
   void* da = ctx->table(ka);
@@ -97,6 +100,7 @@ template <typename T> int Engine<T>::fs_tables(int logN, const C** A, const C** 
     JTB_TRY(ctx->put_table(kb, hb.data(), hb.size() * sizeof(C), &db));
   }
   *A = (const C*)da; *B = (const C*)db; *logL = lL;
+  memo.ctx = (const void*)ctx; memo.logn = logN; memo.a = *A; memo.b = *B;
   return ST_OK;
 }
 
@@ -452,6 +456,23 @@ template <typename T> int Engine<T>::real_inverse_lines(T* a, const Geo& g, i64 
 template <typename T> int Engine<T>::r2r_lines(T* a, const Geo& g, i64 nlines, i64 n, int kind, bool inverse, bool scale) {
   if (n <= 1 || nlines <= 0) return ST_OK;
   const double dn = (double)n;
+  // fused forward kernels (contiguous lines, or the column axis of row-major arrays)
+  {
+    T f0 = 1, f = 1;
+    bool fwd_like = !inverse;
+    if (kind == 3) { fwd_like = true; f0 = f = (inverse && scale) ? (T)(1.0 / dn) : (T)1; }
+    else if (scale) { f0 = (T)std::sqrt(1.0 / dn); f = (T)std::sqrt(2.0 / dn); }
+    if (fwd_like && is_pow2(n)) {
+      bool handled = false;
+      if (g.stride == 1 && g.c[0] == 1 && g.c[1] == 1 && g.c[2] == 1) {
+        JTB_TRY(fast_r2r_rows<T>(*this, a, g.d[3], nlines, n, kind, f0, f, &handled));
+      } else if (g.stride > 1 && g.d[0] == 1 && g.c[1] == 1 && g.c[2] == 1 && g.c[0] == g.stride &&
+                 nlines % g.c[0] == 0 && (nlines == g.c[0] || g.d[3] >= n * g.stride)) {
+        JTB_TRY(fast_r2r_cols<T>(*this, a, n, g.c[0], nlines / g.c[0], g.d[3], kind, f0, f, &handled));
+      }
+      if (handled) return ST_OK;
+    }
+  }
   if (kind == 3) {   // DHT: forward == inverse up to 1/n (dht/DoubleDHT_1D.java:255-270)
     const T fac = (inverse && scale) ? (T)(1.0 / dn) : (T)1;
     return staged_lines<T>(*this, a, g, nlines, n, PRE_R2C, POST_DHT, 0, false, (T)1, (T)1, fac, fac, nullptr);

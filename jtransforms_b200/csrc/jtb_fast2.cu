@@ -14,14 +14,18 @@ template <typename T> struct F2Entry {
   int logn, loge, sin, mode, W, threads, smem;
   void (*kern)(const Fast2Params<T>);
   bool attr_done;
+  i64 min_lines;             // use this variant only for launches with at least this many lines (grid fill)
+  const cx<T>* twg[16];      // per-device base twiddle table
 };
-template <typename T, int LOGN, int LOGE, bool SIN, int MODE, int W> F2Entry<T> mk2() {
+template <typename T, int LOGN, int LOGE, bool SIN, int MODE, int W> F2Entry<T> mk2(i64 min_lines = 0) {
   typedef Sched<LOGN, LOGE> S;
   F2Entry<T> e;
   e.logn = LOGN; e.loge = LOGE; e.sin = SIN; e.mode = MODE; e.W = W; e.threads = W * S::TPL;
   e.smem = (int)((FastAddr<T, S, SIN, W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
   e.kern = fft_fast2_kernel<T, LOGN, LOGE, SIN, MODE, W>;
   e.attr_done = false;
+  e.min_lines = min_lines;
+  for (int d = 0; d < 16; ++d) e.twg[d] = nullptr;
   return e;
 }
 template <typename T> std::vector<F2Entry<T>>& reg2();
@@ -29,10 +33,11 @@ template <> std::vector<F2Entry<double>>& reg2<double>() {
   static std::vector<F2Entry<double>> r = {
       // first pass of the two-pass transform (strided lines, twiddle at the store)
       mk2<double, 6, 3, true, FM_TWID, 32>(), mk2<double, 7, 4, true, FM_TWID, 16>(), mk2<double, 8, 4, true, FM_TWID, 8>(),
-      mk2<double, 9, 3, true, FM_TWID, 8>(), mk2<double, 10, 4, true, FM_TWID, 8>(),
+      mk2<double, 9, 3, true, FM_TWID, 8>(), mk2<double, 10, 4, true, FM_TWID, 8>(8 * 600), mk2<double, 10, 3, true, FM_TWID, 4>(),
       // second pass, contiguous lines with transposed store
       mk2<double, 8, 4, false, FM_TRANSPOSE, 8>(), mk2<double, 9, 3, false, FM_TRANSPOSE, 8>(),
-      mk2<double, 10, 4, false, FM_TRANSPOSE, 8>(), mk2<double, 11, 4, false, FM_TRANSPOSE, 4>(),
+      mk2<double, 10, 4, false, FM_TRANSPOSE, 8>(8 * 600), mk2<double, 10, 3, false, FM_TRANSPOSE, 4>(),
+      mk2<double, 11, 4, false, FM_TRANSPOSE, 4>(),
       // second pass, strided lines (row permutation only)
       mk2<double, 6, 3, true, FM_PLAIN, 32>(), mk2<double, 7, 4, true, FM_PLAIN, 16>(),
       // real-forward rows
@@ -51,9 +56,9 @@ template <> std::vector<F2Entry<float>>& reg2<float>() {
   return r;
 }
 
-template <typename T> F2Entry<T>* find2(int logn, bool sin, int mode) {
+template <typename T> F2Entry<T>* find2(int logn, bool sin, int mode, i64 lines = (1LL << 60)) {
   for (auto& f : reg2<T>())
-    if (f.logn == logn && (f.sin != 0) == sin && f.mode == mode) return &f;
+    if (f.logn == logn && (f.sin != 0) == sin && f.mode == mode && lines >= f.min_lines) return &f;
   return nullptr;
 }
 
@@ -62,7 +67,9 @@ template <typename T> int launch2(Engine<T>& e, F2Entry<T>* f, Fast2Params<T>& p
     JTB_CUDA(cudaFuncSetAttribute(f->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, f->smem));
     f->attr_done = true;
   }
-  JTB_TRY(fast_stage_table<T>(e, f->logn, f->loge, &p.twg));
+  const int dv = e.ctx->device & 15;
+  if (!f->twg[dv]) JTB_TRY(fast_stage_table<T>(e, f->logn, f->loge, &f->twg[dv]));
+  p.twg = f->twg[dv];
   const i64 nblk = (p.nlines + f->W - 1) / f->W;
   if (nblk > 0x7fffffffLL) { set_error("too many lines"); return ST_UNSUPPORTED; }
   static const bool trace = getenv("JTB_TRACE") != nullptr;
@@ -98,8 +105,8 @@ int fast_fourstep_contig(Engine<T>& e, const cx<T>* in, i64 in_dist, cx<T>* out,
   for (int la = logn / 2; la >= 6 && !f1; --la) {
     for (int s = 0; s < 2 && !f1; ++s) {
       const int a = s == 0 ? la : logn - la;   // try the balanced split first, then its mirror
-      F2Entry<T>* x = find2<T>(a, true, FM_TWID);
-      F2Entry<T>* y = find2<T>(logn - a, false, FM_TRANSPOSE);
+      F2Entry<T>* x = find2<T>(a, true, FM_TWID, (l1 - l0) << (logn - a));
+      F2Entry<T>* y = find2<T>(logn - a, false, FM_TRANSPOSE, (l1 - l0) << a);
       if (x && y) { f1 = x; f2 = y; }
     }
   }
@@ -161,23 +168,35 @@ int fast_fourstep_strided(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, int 
   const C *fsA, *fsB;
   int logL;
   JTB_TRY(e.fs_tables(logn, &fsA, &fsB, &logL));
-  // pass 1: lines (c, r2, batch): FFT over r1 (element stride R2*s), twiddle W_n^(k1*r2), a -> work (same offsets)
-  Fast2Params<T> p = blank2<T>();
-  p.in = a; p.out = wk;
-  p.nlines = g.c[0] * R2 * batches; p.c0 = (int)g.c[0]; p.gmod = (int)R2;
-  p.in_gdist = s; p.in_gdist2 = g.d[3]; p.in_cdist = 1; p.in_stride = R2 * s;
-  p.out_gdist = s; p.out_gdist2 = g.d[3]; p.out_cdist = 1; p.out_stride = R2 * s;
-  p.swap_in = inverse;
-  p.fsA = fsA; p.fsB = fsB; p.fs_logL = logL; p.tw_src = 1;
-  JTB_TRY(launch2(e, f1, p));
-  // pass 2: lines (c, k1, batch): FFT over r2 (rows k1*R2 + r2), output element k2 -> row k1 + R1*k2, work -> a
-  Fast2Params<T> q = blank2<T>();
-  q.in = wk; q.out = a;
-  q.nlines = g.c[0] * R1 * batches; q.c0 = (int)g.c[0]; q.gmod = (int)R1;
-  q.in_gdist = R2 * s; q.in_gdist2 = g.d[3]; q.in_cdist = 1; q.in_stride = s;
-  q.out_gdist = s; q.out_gdist2 = g.d[3]; q.out_cdist = 1; q.out_stride = R1 * s;
-  q.swap_out = inverse; q.has_scale = has_scale; q.scale = scale;
-  JTB_TRY(launch2(e, f2, q));
+  // Column strips small enough that the intermediate written by pass 1 is still in L2 (126 MB) when pass 2
+  // reads it: the two passes then cost about one sweep of HBM traffic instead of two.
+  i64 cb = g.c[0];
+  {
+    const char* ev = getenv("JTB_STRIP_MB");
+    const double strip_mb = ev ? atof(ev) : 24.0;
+    const i64 wmax = f1->W > f2->W ? f1->W : f2->W;
+    while (cb > wmax && (cb % 2) == 0 && (double)cb * (double)n * batches * sizeof(C) > strip_mb * 1048576.0) cb /= 2;
+    if (cb % f1->W || cb % f2->W) cb = g.c[0];
+  }
+  for (i64 cs = 0; cs < g.c[0]; cs += cb) {
+    // pass 1: lines (c, r2, batch): FFT over r1 (element stride R2*s), twiddle W_n^(k1*r2), a -> work (same offsets)
+    Fast2Params<T> p = blank2<T>();
+    p.in = a + cs; p.out = wk + cs;
+    p.nlines = cb * R2 * batches; p.c0 = (int)cb; p.gmod = (int)R2;
+    p.in_gdist = s; p.in_gdist2 = g.d[3]; p.in_cdist = 1; p.in_stride = R2 * s;
+    p.out_gdist = s; p.out_gdist2 = g.d[3]; p.out_cdist = 1; p.out_stride = R2 * s;
+    p.swap_in = inverse;
+    p.fsA = fsA; p.fsB = fsB; p.fs_logL = logL; p.tw_src = 1;
+    JTB_TRY(launch2(e, f1, p));
+    // pass 2: lines (c, k1, batch): FFT over r2 (rows k1*R2 + r2), output element k2 -> row k1 + R1*k2, work -> a
+    Fast2Params<T> q = blank2<T>();
+    q.in = wk + cs; q.out = a + cs;
+    q.nlines = cb * R1 * batches; q.c0 = (int)cb; q.gmod = (int)R1;
+    q.in_gdist = R2 * s; q.in_gdist2 = g.d[3]; q.in_cdist = 1; q.in_stride = s;
+    q.out_gdist = s; q.out_gdist2 = g.d[3]; q.out_cdist = 1; q.out_stride = R1 * s;
+    q.swap_out = inverse; q.has_scale = has_scale; q.scale = scale;
+    JTB_TRY(launch2(e, f2, q));
+  }
   *handled = true;
   return ST_OK;
 }
@@ -201,11 +220,164 @@ int fast_rfft_fwd(Engine<T>& e, cx<T>* a, i64 dist, i64 nlines, int logN, bool* 
   return ST_OK;
 }
 
+// ------------------------------------------------------------------------------------------ fused DCT/DST/DHT
+namespace {
+template <typename T> struct RowEntry {
+  int logn, loge, kind, W, threads, smem;
+  void (*kern)(const RowR2RParams<T>);
+  bool attr_done;
+};
+template <typename T, int LOGN, int LOGE, int KIND, int W> RowEntry<T> mkrow() {
+  typedef Sched<LOGN, LOGE> S;
+  RowEntry<T> e;
+  e.logn = LOGN; e.loge = LOGE; e.kind = KIND; e.W = W; e.threads = W * S::TPL;
+  e.smem = (int)((FastAddr<T, S, false, W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
+  e.kern = fft_r2r_row_kernel<T, LOGN, LOGE, KIND, W>;
+  e.attr_done = false;
+  return e;
+}
+#define JTB_ROWS(T, LOGN, LOGE, W) mkrow<T, LOGN, LOGE, RK_DCT, W>(), mkrow<T, LOGN, LOGE, RK_DST, W>(), mkrow<T, LOGN, LOGE, RK_DHT, W>()
+template <typename T> std::vector<RowEntry<T>>& rowreg();
+template <> std::vector<RowEntry<double>>& rowreg<double>() {
+  static std::vector<RowEntry<double>> r = {JTB_ROWS(double, 12, 4, 1), JTB_ROWS(double, 11, 4, 2), JTB_ROWS(double, 10, 4, 4),
+                                            JTB_ROWS(double, 9, 3, 4), JTB_ROWS(double, 8, 4, 8)};
+  return r;
+}
+template <> std::vector<RowEntry<float>>& rowreg<float>() {
+  static std::vector<RowEntry<float>> r = {JTB_ROWS(float, 12, 4, 1), JTB_ROWS(float, 11, 4, 2), JTB_ROWS(float, 10, 4, 4)};
+  return r;
+}
+
+// permuted first passes of the strided DCT/DST columns
+template <typename T> struct PreEntry { int logn, pre; F2Entry<T> e; };
+template <typename T, int LOGN, int LOGE, int W, int PRE> PreEntry<T> mkpre() {
+  typedef Sched<LOGN, LOGE> S;
+  PreEntry<T> x;
+  x.logn = LOGN; x.pre = PRE;
+  F2Entry<T>& e = x.e;
+  e.logn = LOGN; e.loge = LOGE; e.sin = 1; e.mode = FM_TWID; e.W = W; e.threads = W * S::TPL;
+  e.smem = (int)((FastAddr<T, S, true, W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
+  e.kern = fft_fast2_kernel<T, LOGN, LOGE, true, FM_TWID, W, PRE>;
+  e.attr_done = false; e.min_lines = 0;
+  for (int d = 0; d < 16; ++d) e.twg[d] = nullptr;
+  return x;
+}
+template <typename T> std::vector<PreEntry<T>>& prereg();
+template <> std::vector<PreEntry<double>>& prereg<double>() {
+  static std::vector<PreEntry<double>> r = {mkpre<double, 6, 3, 32, PRE_PERM_DCT>(), mkpre<double, 6, 3, 32, PRE_PERM_DST>(),
+                                            mkpre<double, 7, 4, 16, PRE_PERM_DCT>(), mkpre<double, 7, 4, 16, PRE_PERM_DST>()};
+  return r;
+}
+template <> std::vector<PreEntry<float>>& prereg<float>() {
+  static std::vector<PreEntry<float>> r;
+  return r;
+}
+}  // namespace
+
+// forward DCT-II / DST-II / DHT of contiguous real lines (line l at l*dist), in place
+template <typename T>
+int fast_r2r_rows(Engine<T>& e, T* a, i64 dist, i64 nlines, i64 n, int kind, T f0, T f, bool* handled) {
+  *handled = false;
+  if (g_fast2_off || nlines <= 0 || !is_pow2(n) || n < 4 || (dist % 2) || ((uintptr_t)a % sizeof(cx<T>))) return ST_OK;
+  const int logN = ilog2(n) - 1;
+  RowEntry<T>* r = nullptr;
+  for (auto& x : rowreg<T>()) if (x.logn == logN && x.kind == kind) { r = &x; break; }
+  if (!r) return ST_OK;
+  if (!r->attr_done) {
+    JTB_CUDA(cudaFuncSetAttribute(r->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, r->smem));
+    r->attr_done = true;
+  }
+  RowR2RParams<T> p;
+  p.a = a; p.nlines = nlines; p.dist = dist; p.f0 = f0; p.f = f;
+  JTB_TRY(fast_stage_table<T>(e, logN, r->loge, &p.twg));
+  const cx<T>* tw[JTB_MAX_STAGES];
+  JTB_TRY(e.tile_tables(logN, tw, &p.rtw));
+  p.dtw = nullptr;
+  if (kind != RK_DHT) JTB_TRY(e.dct_table(n, &p.dtw));
+  const i64 nblk = (nlines + r->W - 1) / r->W;
+  if (nblk > 0x7fffffffLL) return ST_OK;
+  JTB_LAUNCH(r->kern, (unsigned)nblk, (unsigned)r->threads, (size_t)r->smem, e.st, p);
+  JTB_CUDA(cudaGetLastError());
+  e.ctx->launches++;
+  *handled = true;
+  return ST_OK;
+}
+
+// forward DCT-II / DST-II / DHT along the strided axis of length n of `batches` row-major [n][Cn] real arrays
+// (batch distance bdist reals): two adjacent real columns = one complex column, two-pass complex FFT with the
+// Makhoul row permutation fused into the first pass, then the pair post-pass; column strips sized for L2.
+template <typename T>
+int fast_r2r_cols(Engine<T>& e, T* a, i64 n, i64 Cn, i64 batches, i64 bdist, int kind, T f0, T f, bool* handled) {
+  typedef cx<T> C;
+  *handled = false;
+  if (g_fast2_off || !is_pow2(n) || (Cn % 2) || (bdist % 2) || ((uintptr_t)a % sizeof(C)) || batches < 1) return ST_OK;
+  const int logn = ilog2(n);
+  F2Entry<T>*f1 = nullptr, *f2 = nullptr;
+  for (int la = (logn + 1) / 2; la <= logn - 6 && !f1; ++la) {
+    F2Entry<T>* x = nullptr;
+    if (kind == RK_DHT) x = find2<T>(la, true, FM_TWID);
+    else for (auto& pe : prereg<T>()) if (pe.logn == la && pe.pre == (kind == RK_DCT ? PRE_PERM_DCT : PRE_PERM_DST)) x = &pe.e;
+    F2Entry<T>* y = find2<T>(logn - la, true, FM_PLAIN);
+    if (x && y) { f1 = x; f2 = y; }
+  }
+  if (!f1) return ST_OK;
+  const i64 H = Cn / 2, s = H, R1 = 1LL << f1->logn, R2 = 1LL << f2->logn, bd = bdist / 2;
+  if (H % f1->W || H % f2->W) return ST_OK;
+  const i64 ext = (batches - 1) * bd + n * s;
+  JTB_TRY(e.ctx->ensure(e.ctx->work[WK_FOURSTEP], (size_t)ext * sizeof(C)));
+  JTB_TRY(e.ctx->ensure(e.ctx->work[WK_REAL], (size_t)ext * sizeof(C)));
+  C* wk = (C*)e.ctx->work[WK_FOURSTEP].p;
+  C* wk2 = (C*)e.ctx->work[WK_REAL].p;
+  C* ac = (C*)a;
+  const C *fsA, *fsB, *dtw = nullptr;
+  int logL;
+  JTB_TRY(e.fs_tables(logn, &fsA, &fsB, &logL));
+  if (kind != RK_DHT) JTB_TRY(e.dct_table(n, &dtw));
+  i64 cb = H;
+  {
+    const char* ev = getenv("JTB_STRIP_MB");
+    const double strip_mb = ev ? atof(ev) : 24.0;
+    const i64 wmax = f1->W > f2->W ? f1->W : f2->W;
+    while (cb > wmax && (cb % 2) == 0 && (double)cb * (double)n * batches * sizeof(C) > strip_mb * 1048576.0) cb /= 2;
+    if (cb % f1->W || cb % f2->W) cb = H;
+  }
+  for (i64 cs = 0; cs < H; cs += cb) {
+    Fast2Params<T> p = blank2<T>();
+    p.in = ac + cs; p.out = wk + cs;
+    p.nlines = cb * R2 * batches; p.c0 = (int)cb; p.gmod = (int)R2;
+    p.in_gdist = s; p.in_gdist2 = bd; p.in_cdist = 1; p.in_stride = R2 * s;
+    p.out_gdist = s; p.out_gdist2 = bd; p.out_cdist = 1; p.out_stride = R2 * s;
+    p.fsA = fsA; p.fsB = fsB; p.fs_logL = logL; p.tw_src = 1;
+    p.pre_n = n; p.pre_s = s;
+    JTB_TRY(launch2(e, f1, p));
+    Fast2Params<T> q = blank2<T>();
+    q.in = wk + cs; q.out = wk2 + cs;
+    q.nlines = cb * R1 * batches; q.c0 = (int)cb; q.gmod = (int)R1;
+    q.in_gdist = R2 * s; q.in_gdist2 = bd; q.in_cdist = 1; q.in_stride = s;
+    q.out_gdist = s; q.out_gdist2 = bd; q.out_cdist = 1; q.out_stride = R1 * s;
+    JTB_TRY(launch2(e, f2, q));
+    for (i64 b = 0; b < batches; ++b) {
+      ColPostParams<T> cp;
+      cp.z = wk2 + cs + b * bd; cp.out = ac + cs + b * bd;
+      cp.n = n; cp.cols = cb; cp.s = s; cp.kind = kind; cp.f0 = f0; cp.f = f; cp.dtw = dtw;
+      unsigned gr, bl;
+      grid_for((n / 2 + 1) * cb, &gr, &bl);
+      JTB_LAUNCH(k_r2r_colpost<T>, gr, bl, 0, e.st, cp);
+      JTB_CUDA(cudaGetLastError());
+      e.ctx->launches++;
+    }
+  }
+  *handled = true;
+  return ST_OK;
+}
+
 #define JTB_INST(T)                                                                                                    \
   template int fast_fourstep_contig<T>(Engine<T>&, const cx<T>*, i64, cx<T>*, i64, i64, i64, int, bool, bool, bool, T, \
                                        bool*);                                                                         \
   template int fast_fourstep_strided<T>(Engine<T>&, cx<T>*, const Geo&, i64, int, bool, bool, T, bool*);               \
-  template int fast_rfft_fwd<T>(Engine<T>&, cx<T>*, i64, i64, int, bool*);
+  template int fast_rfft_fwd<T>(Engine<T>&, cx<T>*, i64, i64, int, bool*);                                             \
+  template int fast_r2r_rows<T>(Engine<T>&, T*, i64, i64, i64, int, T, T, bool*);                                      \
+  template int fast_r2r_cols<T>(Engine<T>&, T*, i64, i64, i64, i64, int, T, T, bool*);
 JTB_INST(double)
 JTB_INST(float)
 

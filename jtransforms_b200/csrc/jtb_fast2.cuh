@@ -32,13 +32,18 @@ template <typename T> struct Fast2Params {
   const cx<T>* fsB;   //          W^(l)
   int fs_logL, tw_src;           // idx = tw_src ? g % gmod : c
   const cx<T>* rtw;   // FM_RFFT: exp(-2 pi i k / (2N)), k <= N/2
+  // PRE != 0 (first pass of a long strided DCT/DST column): element j = r1*gmod + (g % gmod) of the column is
+  // read from row perm(j) of the array (Makhoul even/odd permutation), rows are pre_s apart, column length pre_n
+  i64 pre_n, pre_s;
 };
+
+enum { PRE_NONE = 0, PRE_PERM_DCT = 1, PRE_PERM_DST = 2 };
 
 template <typename T> __device__ __forceinline__ cx<T> fs_tw2(const Fast2Params<T>& p, int m) {
   return cmul(__ldg(p.fsA + (m >> p.fs_logL)), __ldg(p.fsB + (m & ((1 << p.fs_logL) - 1))));
 }
 
-template <typename T, int LOGN, int LOGE, bool SIN, int MODE, int W>
+template <typename T, int LOGN, int LOGE, bool SIN, int MODE, int W, int PRE = PRE_NONE>
 __global__ void __launch_bounds__(W * Sched<LOGN, LOGE>::TPL, (Sched<LOGN, LOGE>::E <= 8 ? FastOcc<W * Sched<LOGN, LOGE>::TPL>::MINB
                                                                                       : (FastOcc<W * Sched<LOGN, LOGE>::TPL>::MINB + 1) / 2))
 fft_fast2_kernel(const Fast2Params<T> p) {
@@ -61,7 +66,18 @@ fft_fast2_kernel(const Fast2Params<T> p) {
   const i64 g_hi = g / p.gmod;
   const int g_lo = (int)(g - g_hi * p.gmod);
   C v[S::E];
-  if (valid) {
+  if (valid && PRE != PRE_NONE) {
+    const C* src = p.in + g_hi * p.in_gdist2 + c * p.in_cdist;
+#pragma unroll
+    for (int q = 0; q < S::E; ++q) {
+      const i64 j = (i64)(t + q * S::TPL) * p.gmod + g_lo;
+      const bool second = 2 * j >= p.pre_n;
+      const i64 row = second ? 2 * (p.pre_n - 1 - j) + 1 : 2 * j;
+      C z = src[row * p.pre_s];
+      if (PRE == PRE_PERM_DST && second) { z.x = -z.x; z.y = -z.y; }
+      v[q] = z;
+    }
+  } else if (valid) {
     const C* src = p.in + g_lo * p.in_gdist + g_hi * p.in_gdist2 + c * p.in_cdist;
 #pragma unroll
     for (int q = 0; q < S::E; ++q) v[q] = src[(t + q * S::TPL) * p.in_stride];
@@ -147,6 +163,175 @@ fft_fast2_kernel(const Fast2Params<T> p) {
           dst[k] = cadd(ev, od);
           dst[S::N - k] = mk<T>(ev.x - od.x, -(ev.y - od.y));
         }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Fused forward DCT-II / DST-II / DHT of contiguous real lines of n = 2N reals (N = 2^LOGN):
+//   coalesced load of the line into shared memory -> (Makhoul even/odd permutation for DCT/DST) -> N-point
+//   complex FFT of z[j] = v[2j] + i v[2j+1] -> real split V[k] -> twiddle / cas combination -> store.
+// Replaces per line: dct/DoubleDCT_1D.java:169-194 (pre-butterfly, rftbsub, cftbsub, dctsub, scale),
+// dst/DoubleDST_1D.java:96-160, dht/DoubleDHT_1D.java:94-152.
+enum { RK_DCT = 1, RK_DST = 2, RK_DHT = 3 };
+
+template <typename T> struct RowR2RParams {
+  T* a;                 // lines of n reals, line l at l*dist, transformed in place
+  i64 nlines, dist;
+  T f0, f;              // output factors for index 0 / the others
+  const cx<T>* twg;     // stage twiddles
+  const cx<T>* rtw;     // exp(-2 pi i k / n), k <= N/2
+  const cx<T>* dtw;     // exp(-i pi k / (2n)), k < n   (DCT/DST)
+};
+
+template <typename T, int LOGN, int LOGE, int KIND, int W>
+__global__ void __launch_bounds__(W * Sched<LOGN, LOGE>::TPL, (Sched<LOGN, LOGE>::E <= 8 ? FastOcc<W * Sched<LOGN, LOGE>::TPL>::MINB
+                                                                                      : (FastOcc<W * Sched<LOGN, LOGE>::TPL>::MINB + 1) / 2))
+fft_r2r_row_kernel(const RowR2RParams<T> p) {
+  typedef Sched<LOGN, LOGE> S;
+  typedef cx<T> C;
+  typedef FastAddr<T, S, false, W> A;
+  constexpr int N = S::N, n = 2 * S::N;
+  JTB_DYN_SMEM(smem_raw);
+  C* sm = reinterpret_cast<C*>(smem_raw);
+  T* smr = reinterpret_cast<T*>(smem_raw);          // the real line(s), aliasing the exchange tile
+  C* twt = sm + A::TILE;
+  const int tid = threadIdx.x;
+  const int t = tid % S::TPL, w = tid / S::TPL;
+  for (int i = tid; i < FastTw<S>::COUNT; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
+  const i64 line0 = (i64)blockIdx.x * W;
+  const int nl = (p.nlines - line0 < W) ? (int)(p.nlines - line0) : W;
+  const bool valid = w < nl;
+  // coalesced load: line ww of the CTA at smr[ww*n + i]
+  {
+    const C* src = reinterpret_cast<const C*>(p.a);
+    C* dstc = reinterpret_cast<C*>(smr);
+    for (int idx = tid; idx < W * N; idx += W * S::TPL) {
+      const int ww = idx / N, i = idx - ww * N;
+      if (ww < nl) dstc[ww * N + i] = src[((line0 + ww) * p.dist) / 2 + i];
+    }
+  }
+  __syncthreads();
+  C v[S::E];
+  {
+    const T* x = smr + w * n;
+#pragma unroll
+    for (int q = 0; q < S::E; ++q) {
+      const int j = t + q * S::TPL;
+      C z;
+      if (KIND == RK_DHT) { z.x = x[2 * j]; z.y = x[2 * j + 1]; }
+      else if (2 * j < N) { z.x = x[4 * j]; z.y = x[4 * j + 2]; }
+      else {
+        z.x = x[2 * n - 4 * j - 1]; z.y = x[2 * n - 4 * j - 3];
+        if (KIND == RK_DST) { z.x = -z.x; z.y = -z.y; }
+      }
+      v[q] = valid ? z : mk<T>(0, 0);
+    }
+  }
+  __syncthreads();
+  FastLoop<T, S, 0, false, W>::run(v, sm, twt, t, w);
+  if (S::S > 1) __syncthreads();
+#pragma unroll
+  for (int q = 0; q < S::E; ++q) sm[A::at(t + q * S::TPL, w)] = v[q];
+  __syncthreads();
+  if (!valid) return;
+  T* out = p.a + (line0 + w) * p.dist;
+  const T hf = (T)0.5;
+#pragma unroll
+  for (int q = 0; q < S::E / 2; ++q) {
+    const int k = t + q * S::TPL;     // 0 .. N/2 - 1 ; pair (k, N - k)
+    if (k == 0) {
+      const C z0 = sm[A::at(0, w)];
+      const T V0 = z0.x + z0.y, VN = z0.x - z0.y;          // V[0], V[N] (both real)
+      const C zm = sm[A::at(N / 2, w)];
+      const C Vh = mk<T>(zm.x, -zm.y);                      // V[N/2] = conj Z[N/2]
+      if (KIND == RK_DHT) {
+        out[0] = V0 * p.f; out[N] = VN * p.f;
+        out[N / 2] = (Vh.x - Vh.y) * p.f; out[n - N / 2] = (Vh.x + Vh.y) * p.f;
+      } else {
+        const C uh = cmul(Vh, __ldg(p.dtw + N / 2));
+        const T cN = VN * (T)0.70710678118654752440084436210485L;
+        if (KIND == RK_DCT) {
+          out[0] = V0 * p.f0; out[N] = cN * p.f;
+          out[N / 2] = uh.x * p.f; out[n - N / 2] = -uh.y * p.f;
+        } else {   // DST: output index n-1-k of the DCT result
+          out[n - 1] = V0 * p.f0; out[n - 1 - N] = cN * p.f;
+          out[n - 1 - N / 2] = uh.x * p.f; out[N / 2 - 1] = -uh.y * p.f;
+        }
+      }
+    } else {
+      const C a = sm[A::at(k, w)];
+      const C b = sm[A::at(N - k, w)];
+      const C wk = __ldg(p.rtw + k);
+      const C ev = mk<T>((a.x + b.x) * hf, (a.y - b.y) * hf);
+      const C df = mk<T>((a.x - b.x) * hf, (a.y + b.y) * hf);
+      C od = cmul(df, wk);
+      od = mk<T>(od.y, -od.x);
+      const C Vk = cadd(ev, od);                                   // V[k]
+      const C Vm = mk<T>(ev.x - od.x, -(ev.y - od.y));             // V[N-k]
+      if (KIND == RK_DHT) {
+        out[k] = (Vk.x - Vk.y) * p.f;     out[n - k] = (Vk.x + Vk.y) * p.f;
+        out[N - k] = (Vm.x - Vm.y) * p.f; out[N + k] = (Vm.x + Vm.y) * p.f;
+      } else {
+        const C uk = cmul(Vk, __ldg(p.dtw + k));
+        const C um = cmul(Vm, __ldg(p.dtw + (N - k)));
+        if (KIND == RK_DCT) {
+          out[k] = uk.x * p.f;     out[n - k] = -uk.y * p.f;
+          out[N - k] = um.x * p.f; out[N + k] = -um.y * p.f;
+        } else {
+          out[n - 1 - k] = uk.x * p.f;       out[k - 1] = -uk.y * p.f;
+          out[n - 1 - (N - k)] = um.x * p.f; out[N - k - 1] = -um.y * p.f;
+        }
+      }
+    }
+  }
+}
+
+// Column post-pass of the forward DCT-II / DST-II / DHT along a strided axis of length n where two adjacent real
+// columns were transformed as one complex column Z (length-n complex FFT of the permuted rows):
+//   Va[k] = (Z[k] + conj Z[n-k])/2, Vb[k] = (Z[k] - conj Z[n-k])/(2i);  DCT: C[k] = Re(d^k V[k]), C[n-k] = -Im(d^k V[k])
+// z: [n][ld] complex (rows s apart), out: same shape; DST stores at the reversed row index.
+template <typename T> struct ColPostParams {
+  const cx<T>* z;
+  cx<T>* out;
+  i64 n, cols, s;       // rows, complex columns handled, row distance (complex units)
+  int kind;
+  T f0, f;
+  const cx<T>* dtw;     // exp(-i pi k / (2n))
+};
+
+template <typename T> __global__ void k_r2r_colpost(const ColPostParams<T> p) {
+  typedef cx<T> C;
+  const i64 half = p.n / 2;
+  const i64 total = (half + 1) * p.cols;
+  const T hf = (T)0.5;
+  for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
+    const i64 k = idx / p.cols, c = idx - k * p.cols;
+    const i64 km = (p.n - k) % p.n;
+    const C a = p.z[k * p.s + c];
+    const C b = p.z[km * p.s + c];
+    // Va = (a + conj b)/2 ; Vb = (a - conj b)/(2i)
+    const C Va = mk<T>((a.x + b.x) * hf, (a.y - b.y) * hf);
+    const C Vb = mk<T>((a.y + b.y) * hf, (b.x - a.x) * hf);
+    C o1, o2;       // rows k and n-k of the result, (column 2c, column 2c+1)
+    if (p.kind == RK_DHT) {
+      o1 = mk<T>((Va.x - Va.y) * p.f, (Vb.x - Vb.y) * p.f);
+      o2 = mk<T>((Va.x + Va.y) * p.f, (Vb.x + Vb.y) * p.f);
+      p.out[k * p.s + c] = o1;
+      if (km != k) p.out[km * p.s + c] = o2;
+    } else {
+      const C d = __ldg(p.dtw + k);
+      const C ua = cmul(Va, d), ub = cmul(Vb, d);
+      const T fk = k == 0 ? p.f0 : p.f;
+      o1 = mk<T>(ua.x * fk, ub.x * fk);
+      o2 = mk<T>(-ua.y * p.f, -ub.y * p.f);
+      if (p.kind == RK_DCT) {
+        p.out[k * p.s + c] = o1;
+        if (k != 0 && km != k) p.out[km * p.s + c] = o2;
+      } else {
+        p.out[(p.n - 1 - k) * p.s + c] = o1;
+        if (k != 0 && km != k) p.out[(k - 1) * p.s + c] = o2;
       }
     }
   }

@@ -187,3 +187,26 @@ def test_fast2_rfft(jt, n):
 def test_fast2_real2d(jt):
     pc.fftnd_real(jt, "Double", (8, 4096))
     pc.fftnd_real(jt, "Float", (4, 2048))
+
+
+def test_fast2_fourstep_strided_strips(jt, monkeypatch):
+    monkeypatch.setenv("JTB_STRIP_MB", "2")       # 4 column strips of 32 for 4096 x 128
+    pc.fftnd_complex(jt, "Double", (4096, 128))
+
+
+# fused forward DCT/DST/DHT kernels (rows: fft_r2r_row_kernel; columns: permuted two-pass + pair post-pass)
+@pytest.mark.parametrize("kind", ["DCT", "DST", "DHT"])
+@pytest.mark.parametrize("dims", [(512,), (4, 1024), (4096, 64)])
+def test_fast2_r2r(jt, kind, dims):
+    pc.r2r(jt, "Double", kind, dims)
+
+
+@pytest.mark.parametrize("dims", [(8192,), (8192, 32)])
+def test_fast2_r2r_long(jt, dims):
+    pc.r2r(jt, "Double", "DCT", dims)
+
+
+def test_fast2_r2r_strips_and_float(jt, monkeypatch):
+    monkeypatch.setenv("JTB_STRIP_MB", "1")
+    pc.r2r(jt, "Double", "DCT", (4096, 128))
+    pc.r2r(jt, "Float", "DST", (2, 2048))

@@ -147,6 +147,12 @@ def test_r2r_float(jt, kind):
     pc.r2r(jt, "Float", kind, (128, 512))
 
 
+@pytest.mark.parametrize("kind", ["DCT", "DST", "DHT"])
+@pytest.mark.parametrize("dims", [(4096, 4096), (8192, 512), (4, 4096, 128), (4096, 2, 64)])
+def test_r2r_fused_paths(jt, kind, dims):
+    pc.r2r(jt, "Double", kind, dims)
+
+
 def test_dct2d_8192(jt):
     """config 4 at full size (DCT; DST/DHT share every kernel and are covered at 2048x1024 above)"""
     import scipy.fft as sfft
