@@ -52,6 +52,9 @@ int Ctx::put_table(const std::string& key, const void* host, size_t bytes, void*
   JTB_CUDA(cudaMalloc(&d, bytes < 16 ? 16 : bytes));
   // synchronous copy: the host vector dies when the caller returns
   JTB_CUDA(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
+  // a pageable H2D cudaMemcpy may return before the DMA has landed; kernels on our non-blocking streams would
+  // otherwise be able to read a half-written table
+  JTB_CUDA(cudaDeviceSynchronize());
   tables[key] = d;
   *dev_out = d;
   return ST_OK;

@@ -350,6 +350,11 @@ int Engine<T>::c2c_lines(C* a, const Geo& g, i64 nlines, i64 n, bool inverse, bo
     return c2c_pow2(a, g, a, g, 0, nlines, ilog2(n), f);
   }
   // Bluestein chirp-z (fft/DoubleFFT_1D.java:1920-2107); inverse = swap . forward . swap
+  if (g.stride == 1 && g.c[0] == 1 && g.c[1] == 1 && g.c[2] == 1) {
+    bool handled = false;
+    JTB_TRY(fast_bluestein_contig<T>(*this, a, g.d[3], nlines, n, inverse, has_scale, scale, &handled));
+    if (handled) return ST_OK;
+  }
   const C *bk1, *bk2;
   i64 M;
   JTB_TRY(blue_tables(n, &bk1, &bk2, &M));

@@ -41,8 +41,8 @@ template <> std::vector<F2Entry<double>>& reg2<double>() {
       // second pass, strided lines (row permutation only)
       mk2<double, 6, 3, true, FM_PLAIN, 32>(), mk2<double, 7, 4, true, FM_PLAIN, 16>(),
       // real-forward rows
-      mk2<double, 8, 4, false, FM_RFFT, 8>(), mk2<double, 9, 3, false, FM_RFFT, 4>(), mk2<double, 10, 4, false, FM_RFFT, 4>(),
-      mk2<double, 11, 4, false, FM_RFFT, 2>(), mk2<double, 12, 4, false, FM_RFFT, 1>(),
+      mk2<double, 8, 4, false, FM_RFFT, 8>(), mk2<double, 9, 3, false, FM_RFFT, 4>(), mk2<double, 10, 3, false, FM_RFFT, 2>(),
+      mk2<double, 11, 3, false, FM_RFFT, 1>(), mk2<double, 12, 3, false, FM_RFFT, 1>(),
   };
   return r;
 }
@@ -173,7 +173,7 @@ int fast_fourstep_strided(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, int 
   i64 cb = g.c[0];
   {
     const char* ev = getenv("JTB_STRIP_MB");
-    const double strip_mb = ev ? atof(ev) : 24.0;
+    const double strip_mb = ev ? atof(ev) : 1.0e9;   // off by default: measured slower (launch-bound strips)
     const i64 wmax = f1->W > f2->W ? f1->W : f2->W;
     while (cb > wmax && (cb % 2) == 0 && (double)cb * (double)n * batches * sizeof(C) > strip_mb * 1048576.0) cb /= 2;
     if (cb % f1->W || cb % f2->W) cb = g.c[0];
@@ -239,7 +239,7 @@ template <typename T, int LOGN, int LOGE, int KIND, int W> RowEntry<T> mkrow() {
 #define JTB_ROWS(T, LOGN, LOGE, W) mkrow<T, LOGN, LOGE, RK_DCT, W>(), mkrow<T, LOGN, LOGE, RK_DST, W>(), mkrow<T, LOGN, LOGE, RK_DHT, W>()
 template <typename T> std::vector<RowEntry<T>>& rowreg();
 template <> std::vector<RowEntry<double>>& rowreg<double>() {
-  static std::vector<RowEntry<double>> r = {JTB_ROWS(double, 12, 4, 1), JTB_ROWS(double, 11, 4, 2), JTB_ROWS(double, 10, 4, 4),
+  static std::vector<RowEntry<double>> r = {JTB_ROWS(double, 12, 3, 1), JTB_ROWS(double, 11, 3, 1), JTB_ROWS(double, 10, 3, 2),
                                             JTB_ROWS(double, 9, 3, 4), JTB_ROWS(double, 8, 4, 8)};
   return r;
 }
@@ -336,7 +336,7 @@ int fast_r2r_cols(Engine<T>& e, T* a, i64 n, i64 Cn, i64 batches, i64 bdist, int
   i64 cb = H;
   {
     const char* ev = getenv("JTB_STRIP_MB");
-    const double strip_mb = ev ? atof(ev) : 24.0;
+    const double strip_mb = ev ? atof(ev) : 1.0e9;   // off by default: measured slower (launch-bound strips)
     const i64 wmax = f1->W > f2->W ? f1->W : f2->W;
     while (cb > wmax && (cb % 2) == 0 && (double)cb * (double)n * batches * sizeof(C) > strip_mb * 1048576.0) cb /= 2;
     if (cb % f1->W || cb % f2->W) cb = H;
@@ -371,11 +371,146 @@ int fast_r2r_cols(Engine<T>& e, T* a, i64 n, i64 Cn, i64 batches, i64 bdist, int
   return ST_OK;
 }
 
+// ------------------------------------------------------------------------------------------ fast Bluestein
+namespace {
+template <typename T, int LOGN, int LOGE, int W, int MODE, int PRE> F2Entry<T> mk2x() {
+  typedef Sched<LOGN, LOGE> S;
+  F2Entry<T> e;
+  e.logn = LOGN; e.loge = LOGE; e.sin = 1; e.mode = MODE; e.W = W; e.threads = W * S::TPL;
+  e.smem = (int)((FastAddr<T, S, true, W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
+  e.kern = fft_fast2_kernel<T, LOGN, LOGE, true, MODE, W, PRE>;
+  e.attr_done = false; e.min_lines = 0;
+  for (int d = 0; d < 16; ++d) e.twg[d] = nullptr;
+  return e;
+}
+template <typename T> struct ConvEntry {
+  int logn, loge, W, threads, smem;
+  void (*kern)(const ConvParams<T>);
+  bool attr_done;
+};
+template <typename T, int LOGN, int LOGE, int W> ConvEntry<T> mkconv() {
+  typedef Sched<LOGN, LOGE> S;
+  ConvEntry<T> e;
+  e.logn = LOGN; e.loge = LOGE; e.W = W; e.threads = W * S::TPL;
+  e.smem = (int)((FastAddr<T, S, false, W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
+  e.kern = fft_conv_kernel<T, LOGN, LOGE, W>;
+  e.attr_done = false;
+  return e;
+}
+template <typename T> struct BlueReg {
+  std::vector<F2Entry<T>> first, last;   // strided passes (chirp in / chirp out)
+  std::vector<ConvEntry<T>> mid;
+};
+template <typename T> BlueReg<T>& bluereg();
+template <> BlueReg<double>& bluereg<double>() {
+  static BlueReg<double> r = {
+      {mk2x<double, 9, 3, 8, FM_TWID, PRE_CHIRP>(), mk2x<double, 10, 3, 4, FM_TWID, PRE_CHIRP>()},
+      {mk2x<double, 9, 3, 8, FM_CHIRP_OUT, PRE_NONE>(), mk2x<double, 10, 3, 4, FM_CHIRP_OUT, PRE_NONE>()},
+      {mkconv<double, 10, 3, 2>(), mkconv<double, 11, 3, 1>(), mkconv<double, 12, 3, 1>()}};
+  return r;
+}
+template <> BlueReg<float>& bluereg<float>() {
+  static BlueReg<float> r = {
+      {mk2x<float, 9, 3, 16, FM_TWID, PRE_CHIRP>(), mk2x<float, 10, 4, 16, FM_TWID, PRE_CHIRP>()},
+      {mk2x<float, 9, 3, 16, FM_CHIRP_OUT, PRE_NONE>(), mk2x<float, 10, 4, 16, FM_CHIRP_OUT, PRE_NONE>()},
+      {mkconv<float, 10, 4, 4>(), mkconv<float, 11, 4, 2>(), mkconv<float, 12, 4, 1>()}};
+  return r;
+}
+
+template <typename C> __global__ void k_permute_bk2(const C* bk2, C* out, int logN1, int logN2) {
+  const i64 M = 1LL << (logN1 + logN2), N2 = 1LL << logN2;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (i64)gridDim.x * blockDim.x) {
+    const i64 k1 = i >> logN2, k2 = i & (N2 - 1);
+    out[i] = bk2[k1 + (k2 << logN1)];
+  }
+}
+}  // namespace
+
+// Bluestein chirp-z transform of `nlines` contiguous lines of non-power-of-two length n (line l at l*dist),
+// in place, as three passes over an L2-sized work buffer (see fft_conv_kernel).
+template <typename T>
+int fast_bluestein_contig(Engine<T>& e, cx<T>* a, i64 dist, i64 nlines, i64 n, bool inverse, bool has_scale, T scale,
+                          bool* handled) {
+  typedef cx<T> C;
+  *handled = false;
+  if (g_fast2_off || nlines <= 0 || getenv("JTB_NO_FASTBLUE")) return ST_OK;
+  const i64 M = next_pow2(2 * n - 1);
+  const int logM = ilog2(M);
+  BlueReg<T>& br = bluereg<T>();
+  F2Entry<T>*fa = nullptr, *fc = nullptr;
+  ConvEntry<T>* fb = nullptr;
+  for (size_t i = 0; i < br.first.size() && !fa; ++i)
+    for (auto& m : br.mid)
+      if (br.first[i].logn + m.logn == logM) { fa = &br.first[i]; fc = &br.last[i]; fb = &m; break; }
+  if (!fa) return ST_OK;
+  const i64 N1 = 1LL << fa->logn, N2 = 1LL << fb->logn;
+  if (N2 % fa->W) return ST_OK;
+  const C *bk1, *bk2;
+  i64 M2;
+  JTB_TRY(e.blue_tables(n, &bk1, &bk2, &M2));
+  const std::string kp = mkkey("bk2p", e.pname(), n, fa->logn);
+  C* bk2p = (C*)e.ctx->table(kp);
+  if (!bk2p) {
+    JTB_CUDA(cudaMalloc((void**)&bk2p, (size_t)M * sizeof(C)));
+    unsigned gr, bl;
+    grid_for(M, &gr, &bl);
+    JTB_LAUNCH(k_permute_bk2<C>, gr, bl, 0, e.st, bk2, bk2p, fa->logn, fb->logn);
+    JTB_CUDA(cudaGetLastError());
+    e.ctx->launches++;
+    e.ctx->adopt_table(kp, bk2p);
+  }
+  const C *fsA, *fsB;
+  int logL;
+  JTB_TRY(e.fs_tables(logM, &fsA, &fsB, &logL));
+  const char* ev = getenv("JTB_BLUE_MB");
+  const double mb = ev ? atof(ev) : 64.0;
+  i64 chunk = (i64)(mb * 1048576.0 / ((double)M * sizeof(C)));
+  if (chunk < 1) chunk = 1;
+  if (chunk > nlines) chunk = nlines;
+  JTB_TRY(e.ctx->ensure(e.ctx->work[WK_BLUE], (size_t)chunk * (size_t)M * sizeof(C)));
+  C* wk = (C*)e.ctx->work[WK_BLUE].p;
+  if (!fb->attr_done) {
+    JTB_CUDA(cudaFuncSetAttribute(fb->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fb->smem));
+    fb->attr_done = true;
+  }
+  const cx<T>* twb;
+  JTB_TRY(fast_stage_table<T>(e, fb->logn, fb->loge, &twb));
+  for (i64 c0 = 0; c0 < nlines; c0 += chunk) {
+    const i64 cn = (c0 + chunk < nlines ? c0 + chunk : nlines) - c0;
+    Fast2Params<T> p = blank2<T>();
+    p.in = a + c0 * dist; p.out = wk;
+    p.nlines = cn * N2; p.c0 = (int)N2;
+    p.in_gdist = dist; p.in_cdist = 1; p.in_stride = N2;
+    p.out_gdist = M; p.out_cdist = 1; p.out_stride = N2;
+    p.swap_in = inverse;
+    p.fsA = fsA; p.fsB = fsB; p.fs_logL = logL; p.tw_src = 0;
+    p.chirp = bk1; p.pre_n = n;
+    JTB_TRY(launch2(e, fa, p));
+    ConvParams<T> q;
+    q.a = wk; q.nlines = cn * N1; q.N1 = (int)N1; q.h = bk2p; q.twg = twb; q.fsA = fsA; q.fsB = fsB; q.fs_logL = logL;
+    JTB_LAUNCH(fb->kern, (unsigned)((q.nlines + fb->W - 1) / fb->W), (unsigned)fb->threads, (size_t)fb->smem, e.st, q);
+    JTB_CUDA(cudaGetLastError());
+    e.ctx->launches++;
+    Fast2Params<T> r = blank2<T>();
+    r.in = wk; r.out = a + c0 * dist;
+    r.nlines = cn * N2; r.c0 = (int)N2;
+    r.in_gdist = M; r.in_cdist = 1; r.in_stride = N2;
+    r.out_gdist = dist; r.out_cdist = 1; r.out_stride = N2;
+    r.swap_in = 1; r.swap_out1 = 1; r.swap_out = inverse;
+    r.has_scale = has_scale; r.scale = scale;
+    r.chirp = bk1; r.out_n = n;
+    JTB_TRY(launch2(e, fc, r));
+  }
+  *handled = true;
+  return ST_OK;
+}
+
 #define JTB_INST(T)                                                                                                    \
   template int fast_fourstep_contig<T>(Engine<T>&, const cx<T>*, i64, cx<T>*, i64, i64, i64, int, bool, bool, bool, T, \
                                        bool*);                                                                         \
   template int fast_fourstep_strided<T>(Engine<T>&, cx<T>*, const Geo&, i64, int, bool, bool, T, bool*);               \
   template int fast_rfft_fwd<T>(Engine<T>&, cx<T>*, i64, i64, int, bool*);                                             \
+  template int fast_bluestein_contig<T>(Engine<T>&, cx<T>*, i64, i64, i64, bool, bool, T, bool*);                      \
   template int fast_r2r_rows<T>(Engine<T>&, T*, i64, i64, i64, int, T, T, bool*);                                      \
   template int fast_r2r_cols<T>(Engine<T>&, T*, i64, i64, i64, i64, int, T, T, bool*);
 JTB_INST(double)

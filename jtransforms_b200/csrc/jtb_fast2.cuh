@@ -12,7 +12,7 @@
 
 namespace jtb {
 
-enum { FM_PLAIN = 0, FM_TWID = 1, FM_TRANSPOSE = 2, FM_RFFT = 3 };
+enum { FM_PLAIN = 0, FM_TWID = 1, FM_TRANSPOSE = 2, FM_RFFT = 3, FM_CHIRP_OUT = 4 };
 
 template <typename T> struct Fast2Params {
   const cx<T>* in;
@@ -35,9 +35,15 @@ template <typename T> struct Fast2Params {
   // PRE != 0 (first pass of a long strided DCT/DST column): element j = r1*gmod + (g % gmod) of the column is
   // read from row perm(j) of the array (Makhoul even/odd permutation), rows are pre_s apart, column length pre_n
   i64 pre_n, pre_s;
+  // PRE_CHIRP (first Bluestein pass): element with logical index m = j*in_stride + c*in_cdist is read as
+  // in[m] * conj(chirp[m]) for m < pre_n and as 0 beyond (zero padding to the convolution length).
+  // FM_CHIRP_OUT (last Bluestein pass): out[m] = v * conj(chirp[m]) for m = j*out_stride + c*out_cdist < out_n.
+  const cx<T>* chirp;
+  i64 out_n;
+  int swap_out1;      // FM_CHIRP_OUT: undo the swapped-domain inverse before the chirp multiply
 };
 
-enum { PRE_NONE = 0, PRE_PERM_DCT = 1, PRE_PERM_DST = 2 };
+enum { PRE_NONE = 0, PRE_PERM_DCT = 1, PRE_PERM_DST = 2, PRE_CHIRP = 3 };
 
 template <typename T> __device__ __forceinline__ cx<T> fs_tw2(const Fast2Params<T>& p, int m) {
   return cmul(__ldg(p.fsA + (m >> p.fs_logL)), __ldg(p.fsB + (m & ((1 << p.fs_logL) - 1))));
@@ -66,7 +72,20 @@ fft_fast2_kernel(const Fast2Params<T> p) {
   const i64 g_hi = g / p.gmod;
   const int g_lo = (int)(g - g_hi * p.gmod);
   C v[S::E];
-  if (valid && PRE != PRE_NONE) {
+  if (valid && PRE == PRE_CHIRP) {
+    const C* src = p.in + g_lo * p.in_gdist + g_hi * p.in_gdist2;
+#pragma unroll
+    for (int q = 0; q < S::E; ++q) {
+      const i64 m = (t + q * S::TPL) * p.in_stride + c * p.in_cdist;
+      C z = mk<T>(0, 0);
+      if (m < p.pre_n) {
+        z = src[m];
+        if (p.swap_in) z = cswap(z);
+        z = cmulc(z, __ldg(p.chirp + m));
+      }
+      v[q] = z;
+    }
+  } else if (valid && PRE != PRE_NONE) {
     const C* src = p.in + g_hi * p.in_gdist2 + c * p.in_cdist;
 #pragma unroll
     for (int q = 0; q < S::E; ++q) {
@@ -85,11 +104,29 @@ fft_fast2_kernel(const Fast2Params<T> p) {
 #pragma unroll
     for (int q = 0; q < S::E; ++q) v[q] = mk<T>(0, 0);
   }
-  if (p.swap_in) {
+  if (p.swap_in && PRE != PRE_CHIRP) {
 #pragma unroll
     for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
   }
   FastLoop<T, S, 0, SIN, W>::run(v, sm, twt, t, w);
+  if (MODE == FM_CHIRP_OUT) {
+    if (valid) {
+      C* dst = p.out + g_lo * p.out_gdist + g_hi * p.out_gdist2;
+#pragma unroll
+      for (int q = 0; q < S::E; ++q) {
+        const i64 m = (t + q * S::TPL) * p.out_stride + c * p.out_cdist;
+        if (m < p.out_n) {
+          C z = v[q];
+          if (p.swap_out1) z = cswap(z);
+          z = cmulc(z, __ldg(p.chirp + m));
+          if (p.has_scale) { z.x *= p.scale; z.y *= p.scale; }
+          if (p.swap_out) z = cswap(z);
+          dst[m] = z;
+        }
+      }
+    }
+    return;
+  }
   if (p.has_scale) {
 #pragma unroll
     for (int q = 0; q < S::E; ++q) { v[q].x *= p.scale; v[q].y *= p.scale; }
@@ -169,6 +206,70 @@ fft_fast2_kernel(const Fast2Params<T> p) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Middle pass of the two-pass Bluestein convolution (fft/DoubleFFT_1D.java:1920-2107 does it as cftbsub, a
+// multiply loop and cftfsub): per contiguous row k1 of the [N1][N2] work array
+//   row FFT (second pass of the forward transform, output k2 <-> frequency k1 + N1 k2)  ->  * bk2p[k1][k2]
+//   ->  inverse row FFT (first pass of the inverse transform)  ->  * conj(W_M^(k1 m2))  -> store in place.
+// The frequency-domain product never leaves the SM.
+template <typename T> struct ConvParams {
+  cx<T>* a;              // rows at (g*N1 + k1)*N2, g = transform within the chunk
+  i64 nlines;            // rows
+  int N1;                // rows per transform
+  const cx<T>* h;        // bk2 permuted: h[k1*N2 + k2] = bk2[k1 + N1*k2] (1/M folded in)
+  const cx<T>* twg;
+  const cx<T>* fsA;
+  const cx<T>* fsB;
+  int fs_logL;
+};
+
+template <typename T, int LOGN, int LOGE, int W>
+__global__ void __launch_bounds__(W * Sched<LOGN, LOGE>::TPL, (Sched<LOGN, LOGE>::E <= 8 ? FastOcc<W * Sched<LOGN, LOGE>::TPL>::MINB
+                                                                                      : (FastOcc<W * Sched<LOGN, LOGE>::TPL>::MINB + 1) / 2))
+fft_conv_kernel(const ConvParams<T> p) {
+  typedef Sched<LOGN, LOGE> S;
+  typedef cx<T> C;
+  typedef FastAddr<T, S, false, W> A;
+  JTB_DYN_SMEM(smem_raw);
+  C* sm = reinterpret_cast<C*>(smem_raw);
+  C* twt = sm + A::TILE;
+  const int tid = threadIdx.x;
+  const int t = tid % S::TPL, w = tid / S::TPL;
+  for (int i = tid; i < FastTw<S>::COUNT; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
+  const i64 line = (i64)blockIdx.x * W + w;
+  const bool valid = line < p.nlines;
+  const int k1 = (int)(line % p.N1);
+  C* row = p.a + line * S::N;
+  C v[S::E];
+  if (valid) {
+#pragma unroll
+    for (int q = 0; q < S::E; ++q) v[q] = row[t + q * S::TPL];
+  } else {
+#pragma unroll
+    for (int q = 0; q < S::E; ++q) v[q] = mk<T>(0, 0);
+  }
+  FastLoop<T, S, 0, false, W>::run(v, sm, twt, t, w);
+  if (valid) {
+    const C* h = p.h + (i64)k1 * S::N;
+#pragma unroll
+    for (int q = 0; q < S::E; ++q) v[q] = cswap(cmul(v[q], __ldg(h + t + q * S::TPL)));
+  }
+  if (S::S > 1) __syncthreads();
+  FastLoop<T, S, 0, false, W>::run(v, sm, twt, t, w);
+  if (valid) {
+    // conj(W_M^(k1*m2)), m2 = t + q*TPL, as a chain  conj(W^(k1 t)) * conj(W^(k1 TPL))^q
+    const int L = (1 << p.fs_logL) - 1;
+    const int m0 = k1 * t, ms = k1 * S::TPL;
+    C tw = cmul(__ldg(p.fsA + (m0 >> p.fs_logL)), __ldg(p.fsB + (m0 & L)));
+    const C ws = cmul(__ldg(p.fsA + (ms >> p.fs_logL)), __ldg(p.fsB + (ms & L)));
+#pragma unroll
+    for (int q = 0; q < S::E; ++q) {
+      row[t + q * S::TPL] = cmulc(cswap(v[q]), tw);
+      if (q + 1 < S::E) tw = cmul(tw, ws);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Fused forward DCT-II / DST-II / DHT of contiguous real lines of n = 2N reals (N = 2^LOGN):
 //   coalesced load of the line into shared memory -> (Makhoul even/odd permutation for DCT/DST) -> N-point
 //   complex FFT of z[j] = v[2j] + i v[2j+1] -> real split V[k] -> twiddle / cas combination -> store.
@@ -203,31 +304,33 @@ fft_r2r_row_kernel(const RowR2RParams<T> p) {
   const i64 line0 = (i64)blockIdx.x * W;
   const int nl = (p.nlines - line0 < W) ? (int)(p.nlines - line0) : W;
   const bool valid = w < nl;
-  // coalesced load: line ww of the CTA at smr[ww*n + i]
+  // coalesced load of the lines, stored in shared memory already permuted (Makhoul: v[u] = x[2u],
+  // v[n-1-u] = x[2u+1]; DST additionally negates the odd samples) so that the gather below is one conflict-free
+  // 16-byte read per element: z[j] = (v[2j], v[2j+1])
   {
     const C* src = reinterpret_cast<const C*>(p.a);
-    C* dstc = reinterpret_cast<C*>(smr);
     for (int idx = tid; idx < W * N; idx += W * S::TPL) {
-      const int ww = idx / N, i = idx - ww * N;
-      if (ww < nl) dstc[ww * N + i] = src[((line0 + ww) * p.dist) / 2 + i];
+      const int ww = idx / N, u = idx - ww * N;
+      if (ww < nl) {
+        const C xv = src[((line0 + ww) * p.dist) / 2 + u];
+        if (KIND == RK_DHT) reinterpret_cast<C*>(smr)[ww * N + u] = xv;
+        else {
+          T* vs = smr + ww * n;
+          vs[u] = xv.x;
+          vs[n - 1 - u] = (KIND == RK_DST) ? -xv.y : xv.y;
+        }
+      }
     }
   }
   __syncthreads();
   C v[S::E];
-  {
-    const T* x = smr + w * n;
+  if (valid) {
+    const C* z = reinterpret_cast<const C*>(smr + w * n);
 #pragma unroll
-    for (int q = 0; q < S::E; ++q) {
-      const int j = t + q * S::TPL;
-      C z;
-      if (KIND == RK_DHT) { z.x = x[2 * j]; z.y = x[2 * j + 1]; }
-      else if (2 * j < N) { z.x = x[4 * j]; z.y = x[4 * j + 2]; }
-      else {
-        z.x = x[2 * n - 4 * j - 1]; z.y = x[2 * n - 4 * j - 3];
-        if (KIND == RK_DST) { z.x = -z.x; z.y = -z.y; }
-      }
-      v[q] = valid ? z : mk<T>(0, 0);
-    }
+    for (int q = 0; q < S::E; ++q) v[q] = z[t + q * S::TPL];
+  } else {
+#pragma unroll
+    for (int q = 0; q < S::E; ++q) v[q] = mk<T>(0, 0);
   }
   __syncthreads();
   FastLoop<T, S, 0, false, W>::run(v, sm, twt, t, w);

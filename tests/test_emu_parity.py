@@ -210,3 +210,8 @@ def test_fast2_r2r_strips_and_float(jt, monkeypatch):
     monkeypatch.setenv("JTB_STRIP_MB", "1")
     pc.r2r(jt, "Double", "DCT", (4096, 128))
     pc.r2r(jt, "Float", "DST", (2, 2048))
+
+
+def test_fast_bluestein(jt):
+    pc.fft1d_complex(jt, "Double", 140001)
+    pc.fft1d_batch(jt, "Float", 131073, 2, pad=2)
