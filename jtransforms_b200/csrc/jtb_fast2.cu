@@ -33,10 +33,10 @@ template <> std::vector<F2Entry<double>>& reg2<double>() {
   static std::vector<F2Entry<double>> r = {
       // first pass of the two-pass transform (strided lines, twiddle at the store)
       mk2<double, 6, 3, true, FM_TWID, 32>(), mk2<double, 7, 4, true, FM_TWID, 16>(), mk2<double, 8, 4, true, FM_TWID, 8>(),
-      mk2<double, 9, 3, true, FM_TWID, 8>(), mk2<double, 10, 4, true, FM_TWID, 8>(8 * 600), mk2<double, 10, 3, true, FM_TWID, 4>(),
+      mk2<double, 9, 3, true, FM_TWID, 8>(), mk2<double, 10, 4, true, FM_TWID, 8>(),
       // second pass, contiguous lines with transposed store
       mk2<double, 8, 4, false, FM_TRANSPOSE, 8>(), mk2<double, 9, 3, false, FM_TRANSPOSE, 8>(),
-      mk2<double, 10, 4, false, FM_TRANSPOSE, 8>(8 * 600), mk2<double, 10, 3, false, FM_TRANSPOSE, 4>(),
+      mk2<double, 10, 4, false, FM_TRANSPOSE, 8>(),
       mk2<double, 11, 4, false, FM_TRANSPOSE, 4>(),
       // second pass, strided lines (row permutation only)
       mk2<double, 6, 3, true, FM_PLAIN, 32>(), mk2<double, 7, 4, true, FM_PLAIN, 16>(),
@@ -463,7 +463,7 @@ int fast_bluestein_contig(Engine<T>& e, cx<T>* a, i64 dist, i64 nlines, i64 n, b
   int logL;
   JTB_TRY(e.fs_tables(logM, &fsA, &fsB, &logL));
   const char* ev = getenv("JTB_BLUE_MB");
-  const double mb = ev ? atof(ev) : 64.0;
+  const double mb = ev ? atof(ev) : 1024.0;   // measured: larger chunks win (fewer, longer launches)
   i64 chunk = (i64)(mb * 1048576.0 / ((double)M * sizeof(C)));
   if (chunk < 1) chunk = 1;
   if (chunk > nlines) chunk = nlines;
