@@ -131,16 +131,19 @@ def cpu_reference(w: Workload, budget_s: float = 20.0):
     cores = os.cpu_count() or 1
     rng = np.random.default_rng(2)
     if w.name == "fft3d_512":
-        shape = (256, 512, 512)      # half of the slices: bounded sample, same row/column lengths
-        x = (rng.random(shape) + 1j * rng.random(shape))
-        fn = lambda: sfft.fftn(x, workers=cores)
-        n = float(np.prod(shape))
-        flops = 5.0 * n * math.log2(n)
-        sample = "256x512x512 complex128 (half of the slices), scipy.fft.fftn workers=%d" % cores
+        # C restatement of the reference's algorithm and thread partitioning (oracle/jt_ref.c), full size
+        from oracle import cref
+        x = rng.random(2 * 512 ** 3)
+        fn = lambda: cref.cfft3d(x, 512, 512, 512, -1, cores)
+        flops = w.flops
+        sample = "full 512^3 transform, oracle/jt_ref.c (JTransforms algorithm restated in C), %d threads" % cores
     elif w.name == "fft1d_2p20":
-        x = rng.random(1 << 20) + 1j * rng.random(1 << 20)
-        fn = lambda: sfft.fft(x, workers=cores)
-        flops, sample = w.flops, "full size, scipy.fft.fft"
+        from oracle import cref
+        x = rng.random(2 << 20)
+        nt = min(4, cores)          # the reference never uses more than 4 threads for 1-D (CommonUtils.java:3727-3734)
+        fn = lambda: cref.cfft1d(x, 1 << 20, -1, nt)
+        flops, sample = w.flops, "full size, oracle/jt_ref.c, %d threads (reference maximum for 1-D)" % nt
+        cores = nt
     elif w.name == "fft2d_real_4096":
         x = rng.random((4096, 4096))
         fn = lambda: sfft.rfft2(x, workers=cores)
