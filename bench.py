@@ -130,6 +130,7 @@ def cpu_reference(w: Workload, budget_s: float = 20.0):
     import scipy.fft as sfft
     cores = os.cpu_count() or 1
     rng = np.random.default_rng(2)
+    alt = None
     if w.name == "fft3d_512":
         # C restatement of the reference's algorithm and thread partitioning (oracle/jt_ref.c), full size
         from oracle import cref
@@ -137,12 +138,17 @@ def cpu_reference(w: Workload, budget_s: float = 20.0):
         fn = lambda: cref.cfft3d(x, 512, 512, 512, -1, cores)
         flops = w.flops
         sample = "full 512^3 transform, oracle/jt_ref.c (JTransforms algorithm restated in C), %d threads" % cores
+        z = x.view(np.complex128).reshape(512, 512, 512)
+        alt = (lambda: sfft.fftn(z, workers=cores, overwrite_x=True),
+               "full 512^3 transform, scipy.fft.fftn (pocketfft) workers=%d" % cores)
     elif w.name == "fft1d_2p20":
         from oracle import cref
         x = rng.random(2 << 20)
         nt = min(4, cores)          # the reference never uses more than 4 threads for 1-D (CommonUtils.java:3727-3734)
         fn = lambda: cref.cfft1d(x, 1 << 20, -1, nt)
         flops, sample = w.flops, "full size, oracle/jt_ref.c, %d threads (reference maximum for 1-D)" % nt
+        z1 = x.view(np.complex128)
+        alt = (lambda: sfft.fft(z1, workers=nt), "full size, scipy.fft.fft (pocketfft) workers=%d" % nt)
         cores = nt
     elif w.name == "fft2d_real_4096":
         x = rng.random((4096, 4096))
@@ -158,15 +164,23 @@ def cpu_reference(w: Workload, budget_s: float = 20.0):
         fn = lambda: sfft.fft(x, axis=-1, workers=cores)
         flops = 5.0 * 1000003 * math.log2(1000003) * 4
         sample = "4 transforms of n=1000003 complex64, scipy.fft.fft workers=%d" % cores
-    fn()
-    best, t_used, reps = 1e30, 0.0, 0
-    while t_used < budget_s and reps < 5:
-        t0 = time.perf_counter()
-        fn()
-        dt = time.perf_counter() - t0
-        best = min(best, dt)
-        t_used += dt
-        reps += 1
+    def best_of(f, budget):
+        f()
+        b, used, reps = 1e30, 0.0, 0
+        while used < budget and reps < 5:
+            t0 = time.perf_counter()
+            f()
+            dt = time.perf_counter() - t0
+            b = min(b, dt)
+            used += dt
+            reps += 1
+        return b
+    best = best_of(fn, budget_s / 2)
+    if alt is not None:
+        # two CPU implementations of the same transform are available: report the FASTER one as the baseline
+        b2 = best_of(alt[0], budget_s / 2)
+        if b2 < best:
+            best, sample = b2, alt[1]
     return {"value": flops / best / 1e9, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
             "seconds": best}
 
