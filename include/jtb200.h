@@ -73,6 +73,12 @@ int jtb_lines_c2c_device(int prec, int device, void* dev_a, int64_t n, int64_t n
  * Replaces cdft3db_subth's slice-axis gather (fft/DoubleFFT_3D.java:6318-6520) across devices. */
 int jtb_fft3d_k2_scatter(int prec, int device, const void* local_a, int64_t Ls, int64_t R, int64_t C, int nranks,
                          int rank, void* const* recv_ptrs, int inverse, void* stream);
+/* Both in-slice passes (rows, then columns) of `nslices` rows x cols slices in place; recv_ptrs == NULL keeps the
+ * result local, otherwise the column pass stores straight into the peers' receive buffers as
+ * jtb_fft3d_k2_scatter does.  512 x 512 double slices run as ONE persistent cooperative kernel that keeps the
+ * intermediate in L2 (xdft3da_subth2, fft/DoubleFFT_3D.java:5505-5713). */
+int jtb_fft2d_slices_device(int prec, int device, void* dev_a, int64_t nslices, int64_t rows, int64_t cols, int nranks,
+                            int rank, void* const* recv_ptrs, int inverse, void* stream);
 /* device-side barrier between the ranks on `stream`: publishes `epoch` into every peer's flag array and waits
  * for all peers to publish it (flag_ptrs[h] = peer-mapped int64[nranks] of rank h, zero-initialised). */
 int jtb_peer_barrier(int device, void* const* flag_ptrs, int nranks, int rank, int64_t epoch, void* stream);

@@ -33,8 +33,12 @@ template <typename T> int nd_c2c(Engine<T>& e, cx<T>* a, int rank, const i64* d,
     return e.c2c_lines(a, geo_make(Cn, 1, R * Cn, Cn), Cn, R, inverse, scale, (T)(1.0 / ((double)R * (double)Cn)));
   }
   const i64 S = d[0], R = d[1], Cn = d[2];
-  JTB_TRY(e.c2c_lines(a, geo_contig(Cn), S * R, Cn, inverse, false, (T)1));
-  JTB_TRY(e.c2c_lines(a, geo_make(Cn, 1, R * Cn, Cn), Cn * S, R, inverse, false, (T)1));
+  bool fused = false;
+  if (R == Cn) JTB_TRY(fast_slice2d<T>(e, a, S, R, inverse, false, (T)1, 1, 0, nullptr, &fused));   // rows + columns per slice, via L2
+  if (!fused) {
+    JTB_TRY(e.c2c_lines(a, geo_contig(Cn), S * R, Cn, inverse, false, (T)1));
+    JTB_TRY(e.c2c_lines(a, geo_make(Cn, 1, R * Cn, Cn), Cn * S, R, inverse, false, (T)1));
+  }
   return e.c2c_lines(a, geo_make(R * Cn, 1, S * R * Cn, R * Cn), R * Cn, S, inverse, scale,
                      (T)(1.0 / ((double)S * (double)R * (double)Cn)));
 }
@@ -287,6 +291,29 @@ int jtb_lines_c2c_device(int prec, int device, void* dev_a, int64_t n, int64_t n
   }
   Engine<float> e(c, (cudaStream_t)stream);
   return e.c2c_lines((float2*)dev_a, g, nlines, n, inverse != 0, has_scale, (float)scale);
+}
+
+int jtb_fft2d_slices_device(int prec, int device, void* dev_a, int64_t nslices, int64_t rows, int64_t cols, int nranks,
+                            int rank, void* const* recv_ptrs, int inverse, void* stream) {
+  if (!dev_a || nslices < 1 || rows < 2 || cols < 2) { set_error("bad argument"); return ST_ARG; }
+  Ctx* c = get_ctx(device);
+  if (!c) return ST_CUDA;
+  std::lock_guard<std::mutex> lk(c->mu);
+  JTB_CUDA(cudaSetDevice(device));
+  if (prec != JTB_F64 && prec != JTB_F32) { set_error("bad precision"); return ST_ARG; }
+  bool fused = false;
+  if (prec == JTB_F64) {
+    Engine<double> e(c, (cudaStream_t)stream);
+    if (rows == cols) JTB_TRY(fast_slice2d<double>(e, (double2*)dev_a, nslices, rows, inverse != 0, false, 1.0, nranks, rank, recv_ptrs, &fused));
+    if (fused) return ST_OK;
+    JTB_TRY(e.c2c_lines((double2*)dev_a, geo_contig(cols), nslices * rows, cols, inverse != 0, false, 1.0));
+    if (recv_ptrs) return fast_scatter<double>(e, (const double2*)dev_a, nslices, rows, cols, nranks, rank, recv_ptrs, inverse != 0);
+    return e.c2c_lines((double2*)dev_a, geo_make(cols, 1, rows * cols, cols), cols * nslices, rows, inverse != 0, false, 1.0);
+  }
+  Engine<float> e(c, (cudaStream_t)stream);
+  JTB_TRY(e.c2c_lines((float2*)dev_a, geo_contig(cols), nslices * rows, cols, inverse != 0, false, 1.0f));
+  if (recv_ptrs) return fast_scatter<float>(e, (const float2*)dev_a, nslices, rows, cols, nranks, rank, recv_ptrs, inverse != 0);
+  return e.c2c_lines((float2*)dev_a, geo_make(cols, 1, rows * cols, cols), cols * nslices, rows, inverse != 0, false, 1.0f);
 }
 
 int jtb_fft3d_k2_scatter(int prec, int device, const void* local_a, int64_t Ls, int64_t R, int64_t Cn, int nranks,

@@ -117,6 +117,9 @@ int fast_r2r_cols(Engine<T>& e, T* a, i64 n, i64 Cn, i64 batches, i64 bdist, int
 template <typename T>
 int fast_bluestein_contig(Engine<T>& e, cx<T>* a, i64 dist, i64 nlines, i64 n, bool inverse, bool has_scale, T scale,
                           bool* handled);
+template <typename T>
+int fast_slice2d(Engine<T>& e, cx<T>* a, i64 nslices, i64 N, bool inverse, bool has_scale, T scale, int nranks, int rank,
+                 void* const* peers, bool* handled);   // jtb_fast.cu
 int peer_barrier(Ctx* ctx, cudaStream_t st, void* const* flag_ptrs, int nranks, int rank, long long epoch);
 
 extern template struct Engine<double>;

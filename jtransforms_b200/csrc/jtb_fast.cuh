@@ -217,6 +217,110 @@ fft_scatter_kernel(const ScatterParams<T> p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Both in-slice passes of a 3-D (or batched 2-D) transform in ONE persistent kernel: a team of `team` CTAs owns
+// one N x N slice at a time, transforms its rows (phase A), meets at a team barrier (one counter per slice in
+// global memory), then transforms its columns (phase B).  The intermediate never has to come back from HBM: a
+// slice is 4 MiB (512^2 complex doubles) and all teams together keep well under the 126 MB L2, so phase B reads
+// L2 hits and phase A's dirty lines are overwritten before they are evicted.  Replaces xdft3da_subth2
+// (fft/DoubleFFT_3D.java:5505-5713).  With `scatter` the phase-B stores are the slab all-to-all (see
+// fft_scatter_kernel).  Launched cooperatively so that every CTA of a team is resident.
+template <typename T> struct Slice2DParams {
+  cx<T>* a;            // [nslices][N][N]
+  int nslices, team;
+  int* counters;       // nslices arrival counters, zeroed before the launch
+  int* err;
+  const cx<T>* twg;
+  int inverse;
+  int has_scale; T scale;
+  int scatter, logRh, slice0;
+  cx<T>* peer[8];
+};
+
+template <typename T, int LOGN, int LOGE, int W>
+__global__ void __launch_bounds__(W * Sched<LOGN, LOGE>::TPL, 2) fft_slice2d_kernel(const Slice2DParams<T> p) {
+#ifndef JTB_EMU
+  typedef Sched<LOGN, LOGE> S;
+  typedef cx<T> C;
+  typedef FastAddr<T, S, false, W> AC;
+  typedef FastAddr<T, S, true, W> AS;
+  constexpr int N = S::N;
+  JTB_DYN_SMEM(smem_raw);
+  C* sm = reinterpret_cast<C*>(smem_raw);
+  C* twt = sm + (AC::TILE > AS::TILE ? AC::TILE : AS::TILE);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < FastTw<S>::COUNT; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
+  const int nteams = gridDim.x / p.team;
+  const int team = blockIdx.x / p.team, rank = blockIdx.x - team * p.team;
+  if (team >= nteams) return;
+  const int per = N / p.team;                 // rows (phase A) / columns (phase B) per CTA
+  C v[S::E];
+  for (int slice = team; slice < p.nslices; slice += nteams) {
+    C* sl = p.a + (i64)slice * N * N;
+    // ---- phase A: contiguous rows
+    {
+      const int t = tid % S::TPL, w = tid / S::TPL;
+      for (int r0 = rank * per; r0 < (rank + 1) * per; r0 += W) {
+        C* base = sl + (i64)(r0 + w) * N;
+#pragma unroll
+        for (int q = 0; q < S::E; ++q) v[q] = base[t + q * S::TPL];
+        if (p.inverse) {
+#pragma unroll
+          for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
+        }
+        FastLoop<T, S, 0, false, W>::run(v, sm, twt, t, w);
+#pragma unroll
+        for (int q = 0; q < S::E; ++q) base[t + q * S::TPL] = v[q];   // stays in the swapped domain for phase B
+        __syncthreads();
+      }
+    }
+    // ---- team barrier: all rows of this slice are written (and visible at L2) before any column is read
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(p.counters + slice, 1);
+      const long long t0 = clock64();
+      while (*((volatile int*)(p.counters + slice)) < p.team) {
+        if (clock64() - t0 > 8000000000LL) { *p.err = 1; break; }
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    // ---- phase B: columns, W adjacent columns per pass
+    {
+      const int w = tid % W, t = tid / W;
+      for (int c0 = rank * per; c0 < (rank + 1) * per; c0 += W) {
+        const C* base = sl + c0 + w;
+#pragma unroll
+        for (int q = 0; q < S::E; ++q) v[q] = __ldcg(base + (i64)(t + q * S::TPL) * N);
+        FastLoop<T, S, 0, true, W>::run(v, sm, twt, t, w);
+        if (p.has_scale) {
+#pragma unroll
+          for (int q = 0; q < S::E; ++q) { v[q].x *= p.scale; v[q].y *= p.scale; }
+        }
+        if (p.inverse) {
+#pragma unroll
+          for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
+        }
+        if (p.scatter) {
+          const int Rh = 1 << p.logRh;
+          const i64 row0 = (i64)(p.slice0 + slice) * Rh;
+#pragma unroll
+          for (int q = 0; q < S::E; ++q) {
+            const int k2 = t + q * S::TPL;
+            p.peer[k2 >> p.logRh][(row0 + (k2 & (Rh - 1))) * N + c0 + w] = v[q];
+          }
+        } else {
+          C* dst = sl + c0 + w;
+#pragma unroll
+          for (int q = 0; q < S::E; ++q) dst[(i64)(t + q * S::TPL) * N] = v[q];
+        }
+        __syncthreads();
+      }
+    }
+  }
+#endif
+}
+
 // cross-GPU barrier: thread h publishes `epoch` into rank h's flag array (slot = my rank) and waits until
 // rank h has published it into mine.  flags are peer-mapped int64[nranks] arrays, monotonically increasing.
 struct PeerFlags { long long* f[8]; };

@@ -108,18 +108,26 @@ class SlabFFT3D:
         """a: local slab [Ls][R][C] interleaved complex (2*Ls*R*C reals), transformed in place for P == 1.
         Returns the tensor holding the k2-slabbed result [S][Rh][C] (``a`` itself when P == 1)."""
         S, R, Cn, P, Ls, Rh = self.S, self.R, self.Cn, self.P, self.Ls, self.Rh
-        self._lines(a, Cn, Ls * R, 1, 0, Cn, 1)                       # k3: contiguous rows
-        if P > 1 and self.exchange == "p2p":
-            # fused: k2 pass whose stores ARE the all-to-all (NVLink peer stores), then a device-side barrier
-            b = self.step & 1
-            self.step += 1
-            stream = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
-            _lib.check(self.lib.jtb_fft3d_k2_scatter(self.prec, self.dev, C.c_void_p(a.data_ptr()), Ls, R, Cn, P,
-                                                     self.rank, self._peer["arr"][b], 0, stream))
+        stream = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream if a.is_cuda else 0)
+        if P == 1 or self.exchange == "p2p":
+            # both in-slice passes in one call (one persistent kernel for 512^2 double slices); with P > 1 the
+            # column pass stores ARE the all-to-all (NVLink peer stores)
+            if P > 1:
+                b = self.step & 1
+                self.step += 1
+                peers = self._peer["arr"][b]
+            else:
+                peers = None
+            _lib.check(self.lib.jtb_fft2d_slices_device(self.prec, self.dev, C.c_void_p(a.data_ptr()), Ls, R, Cn, P,
+                                                        self.rank, peers, 0, stream))
+            if P == 1:
+                self._lines(a, S, R * Cn, R * Cn, 1, S * R * Cn, R * Cn)  # k1: across slices
+                return a
             _lib.check(self.lib.jtb_peer_barrier(self.dev, self._peer["arr"][2], P, self.rank, self.step, stream))
             recv = self._recv_tensor(b)
             self._lines(recv, S, Rh * Cn, Rh * Cn, 1, S * Rh * Cn, Rh * Cn)
             return recv
+        self._lines(a, Cn, Ls * R, 1, 0, Cn, 1)                       # k3: contiguous rows
         self._lines(a, R, Cn * Ls, Cn, 1, R * Cn, Cn)                 # k2: columns inside each slice
         if P == 1:
             self._lines(a, S, R * Cn, R * Cn, 1, S * R * Cn, R * Cn)  # k1: across slices
