@@ -73,6 +73,10 @@ int jtb_lines_c2c_device(int prec, int device, void* dev_a, int64_t n, int64_t n
  * Replaces cdft3db_subth's slice-axis gather (fft/DoubleFFT_3D.java:6318-6520) across devices. */
 int jtb_fft3d_k2_scatter(int prec, int device, const void* local_a, int64_t Ls, int64_t R, int64_t C, int nranks,
                          int rank, void* const* recv_ptrs, int inverse, void* stream);
+/* same for a chunk of the local slab: local_a points at `Ls` slices whose first one has GLOBAL slice index
+ * slice_base (lets the caller pipeline the k3 pass of one chunk under the exchange of the previous one) */
+int jtb_fft3d_k2_scatter_chunk(int prec, int device, const void* local_a, int64_t Ls, int64_t slice_base, int64_t R,
+                               int64_t C, int nranks, void* const* recv_ptrs, int inverse, void* stream);
 /* Both in-slice passes (rows, then columns) of `nslices` rows x cols slices in place; recv_ptrs == NULL keeps the
  * result local, otherwise the column pass stores straight into the peers' receive buffers as
  * jtb_fft3d_k2_scatter does.  512 x 512 double slices run as ONE persistent cooperative kernel that keeps the

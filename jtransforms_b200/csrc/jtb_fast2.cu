@@ -274,6 +274,33 @@ template <> std::vector<PreEntry<float>>& prereg<float>() {
 }
 }  // namespace
 
+namespace {
+template <typename T> struct PairEntry {
+  int logn, loge, W, threads, smem;
+  void (*kern)(const ColPairParams<T>);
+  bool attr_done;
+};
+template <typename T, int LOGN, int LOGE, int W> PairEntry<T> mkpair() {
+  typedef Sched<LOGN, LOGE> S;
+  PairEntry<T> e;
+  e.logn = LOGN; e.loge = LOGE; e.W = W; e.threads = 2 * W * S::TPL;
+  e.smem = (int)((FastAddr<T, S, true, 2 * W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
+  e.kern = fft_colpair_kernel<T, LOGN, LOGE, W>;
+  e.attr_done = false;
+  return e;
+}
+template <typename T> std::vector<PairEntry<T>>& pairreg();
+template <> std::vector<PairEntry<double>>& pairreg<double>() {
+  static std::vector<PairEntry<double>> r = {mkpair<double, 6, 3, 32>(), mkpair<double, 7, 4, 16>()};
+  return r;
+}
+template <> std::vector<PairEntry<float>>& pairreg<float>() {
+  static std::vector<PairEntry<float>> r;
+  return r;
+}
+
+}  // namespace
+
 // forward DCT-II / DST-II / DHT of contiguous real lines (line l at l*dist), in place
 template <typename T>
 int fast_r2r_rows(Engine<T>& e, T* a, i64 dist, i64 nlines, i64 n, int kind, T f0, T f, bool* handled) {
@@ -323,6 +350,9 @@ int fast_r2r_cols(Engine<T>& e, T* a, i64 n, i64 Cn, i64 batches, i64 bdist, int
   if (!f1) return ST_OK;
   const i64 H = Cn / 2, s = H, R1 = 1LL << f1->logn, R2 = 1LL << f2->logn, bd = bdist / 2;
   if (H % f1->W || H % f2->W) return ST_OK;
+  PairEntry<T>* fp = nullptr;
+  if (!getenv("JTB_NO_COLPAIR"))
+    for (auto& x : pairreg<T>()) if (x.logn == f2->logn && H % x.W == 0) { fp = &x; break; }
   const i64 ext = (batches - 1) * bd + n * s;
   JTB_TRY(e.ctx->ensure(e.ctx->work[WK_FOURSTEP], (size_t)ext * sizeof(C)));
   JTB_TRY(e.ctx->ensure(e.ctx->work[WK_REAL], (size_t)ext * sizeof(C)));
@@ -350,6 +380,23 @@ int fast_r2r_cols(Engine<T>& e, T* a, i64 n, i64 Cn, i64 batches, i64 bdist, int
     p.fsA = fsA; p.fsB = fsB; p.fs_logL = logL; p.tw_src = 1;
     p.pre_n = n; p.pre_s = s;
     JTB_TRY(launch2(e, f1, p));
+    if (fp) {
+      // second pass + pair post-pass in one kernel, writing the final result
+      if (!fp->attr_done) {
+        JTB_CUDA(cudaFuncSetAttribute(fp->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fp->smem));
+        fp->attr_done = true;
+      }
+      ColPairParams<T> cp;
+      cp.z = wk + cs; cp.out = ac + cs; cp.s = s; cp.bdist = bd;
+      cp.R1 = (int)R1; cp.cols = (int)cb; cp.batches = (int)batches; cp.kind = kind; cp.f0 = f0; cp.f = f; cp.dtw = dtw;
+      JTB_TRY(fast_stage_table<T>(e, fp->logn, fp->loge, &cp.twg));
+      const i64 nblk = (cb / fp->W) * (R1 / 2 + 1) * batches;
+      if (nblk > 0x7fffffffLL) { set_error("too many column tiles"); return ST_UNSUPPORTED; }
+      JTB_LAUNCH(fp->kern, (unsigned)nblk, (unsigned)fp->threads, (size_t)fp->smem, e.st, cp);
+      JTB_CUDA(cudaGetLastError());
+      e.ctx->launches++;
+      continue;
+    }
     Fast2Params<T> q = blank2<T>();
     q.in = wk + cs; q.out = wk2 + cs;
     q.nlines = cb * R1 * batches; q.c0 = (int)cb; q.gmod = (int)R1;

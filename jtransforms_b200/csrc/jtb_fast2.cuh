@@ -391,6 +391,86 @@ fft_r2r_row_kernel(const RowR2RParams<T> p) {
   }
 }
 
+// Second column pass of the strided forward DCT-II / DST-II / DHT fused with the pair post-pass: a CTA transforms
+// the two lines k1 and R1-k1 (length R2, rows k1*R2 + r2) of W adjacent complex columns, so that every output row
+// k = k1 + R1*k2 finds its partner n-k = (R1-k1) + R1*(R2-1-k2) in the same CTA (through shared memory) and the
+// final real results are stored directly -- no separate sweep for k_r2r_colpost.
+template <typename T> struct ColPairParams {
+  const cx<T>* z;       // first-pass output, rows s apart, batch bdist apart
+  cx<T>* out;
+  i64 s, bdist;
+  int R1, cols, batches; // lines per column, complex columns in this launch, arrays
+  int kind;
+  T f0, f;
+  const cx<T>* twg;
+  const cx<T>* dtw;
+};
+
+template <typename T, int LOGN, int LOGE, int W>
+__global__ void __launch_bounds__(2 * W * Sched<LOGN, LOGE>::TPL, 2) fft_colpair_kernel(const ColPairParams<T> p) {
+  typedef Sched<LOGN, LOGE> S;
+  typedef cx<T> C;
+  constexpr int R2 = S::N, W2 = 2 * W;            // the exchange tile holds 2*W "columns": (u, w)
+  typedef FastAddr<T, S, true, W2> A;
+  JTB_DYN_SMEM(smem_raw);
+  C* sm = reinterpret_cast<C*>(smem_raw);
+  C* twt = sm + A::TILE;
+  const int tid = threadIdx.x;
+  const int wu = tid % W2, t = tid / W2;          // wu = u*W + w
+  const int u = wu / W, w = wu - u * W;
+  for (int i = tid; i < FastTw<S>::COUNT; i += W2 * S::TPL) twt[i] = __ldg(p.twg + i);
+  // block -> (column group, line pair, batch)
+  const int groups = p.cols / W, pairs = p.R1 / 2 + 1;
+  int b = blockIdx.x;
+  const int cg = b % groups; b /= groups;
+  const int pr = b % pairs;
+  const int batch = b / pairs;
+  const int k1 = u == 0 ? pr : (p.R1 - pr) % p.R1;
+  const i64 n = (i64)p.R1 * R2;
+  const C* src = p.z + batch * p.bdist + (i64)k1 * R2 * p.s + cg * W + w;
+  C v[S::E];
+#pragma unroll
+  for (int q = 0; q < S::E; ++q) v[q] = src[(i64)(t + q * S::TPL) * p.s];
+  FastLoop<T, S, 0, true, W2>::run(v, sm, twt, t, wu);
+  if (S::S > 1) __syncthreads();
+#pragma unroll
+  for (int q = 0; q < S::E; ++q) sm[A::at(t + q * S::TPL, wu)] = v[q];
+  __syncthreads();
+  const bool dup = (u == 1) && (k1 == pr);          // self-paired line handled twice: second copy does not store
+  if (dup) return;
+  C* dst = p.out + batch * p.bdist + cg * W + w;
+  const T hf = (T)0.5;
+#pragma unroll
+  for (int q = 0; q < S::E; ++q) {
+    const int k2 = t + q * S::TPL;
+    const i64 k = k1 + (i64)p.R1 * k2;
+    // partner Z[n-k]
+    int pu, pk2;
+    if (k1 == 0) { pu = u; pk2 = (R2 - k2) % R2; }
+    else { pu = (p.R1 - k1 == k1) ? u : 1 - u; pk2 = R2 - 1 - k2; }
+    C a = v[q];
+    C bq = sm[A::at(pk2, pu * W + w)];
+    const bool upper = 2 * k > n;
+    const i64 kk = upper ? n - k : k;
+    if (upper) { const C tmp = a; a = bq; bq = tmp; }
+    const C Va = mk<T>((a.x + bq.x) * hf, (a.y - bq.y) * hf);
+    const C Vb = mk<T>((a.y + bq.y) * hf, (bq.x - a.x) * hf);
+    C o;
+    i64 row;
+    if (p.kind == RK_DHT) {
+      o = upper ? mk<T>((Va.x + Va.y) * p.f, (Vb.x + Vb.y) * p.f) : mk<T>((Va.x - Va.y) * p.f, (Vb.x - Vb.y) * p.f);
+      row = k;
+    } else {
+      const C d = __ldg(p.dtw + kk);
+      const C ua = cmul(Va, d), ub = cmul(Vb, d);
+      const T fk = kk == 0 ? p.f0 : p.f;
+      o = upper ? mk<T>(-ua.y * p.f, -ub.y * p.f) : mk<T>(ua.x * fk, ub.x * fk);
+      row = p.kind == RK_DCT ? k : n - 1 - k;
+    }
+    dst[row * p.s] = o;
+  }
+}
+
 // Column post-pass of the forward DCT-II / DST-II / DHT along a strided axis of length n where two adjacent real
 // columns were transformed as one complex column Z (length-n complex FFT of the permuted rows):
 //   Va[k] = (Z[k] + conj Z[n-k])/2, Vb[k] = (Z[k] - conj Z[n-k])/(2i);  DCT: C[k] = Re(d^k V[k]), C[n-k] = -Im(d^k V[k])

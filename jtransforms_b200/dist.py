@@ -43,6 +43,9 @@ class SlabFFT3D:
         self.exchange = exchange
         self.step = 0
         self._peer = None
+        self._side = None
+        import os as _os
+        self.chunks = int(_os.environ.get("JTB_SLAB_CHUNKS", "1"))   # >1: pipeline k3 under the exchange (measured: no gain)
         if self.P > 1 and exchange == "p2p":
             self._setup_p2p()
 
@@ -118,8 +121,30 @@ class SlabFFT3D:
                 peers = self._peer["arr"][b]
             else:
                 peers = None
-            _lib.check(self.lib.jtb_fft2d_slices_device(self.prec, self.dev, C.c_void_p(a.data_ptr()), Ls, R, Cn, P,
-                                                        self.rank, peers, 0, stream))
+            if P > 1 and self.chunks > 1 and Ls % self.chunks == 0 and a.is_cuda:
+                # pipeline: k3 of chunk i+1 (HBM-bound, main stream) runs under the fused k2+exchange of chunk i
+                # (NVLink-bound, side stream)
+                main = torch.cuda.current_stream(a.device)
+                if self._side is None:
+                    # k3 runs on a HIGH-priority stream so its CTAs are scheduled ahead of the pending CTAs of the
+                    # long NVLink-bound exchange kernel of the previous chunk
+                    self._side = torch.cuda.Stream(device=a.device, priority=-1)
+                    self._evs = [torch.cuda.Event() for _ in range(self.chunks)]
+                hp, per = self._side, Ls // self.chunks
+                hp.wait_stream(main)
+                esz = a.element_size()
+                for i in range(self.chunks):
+                    ptr = a.data_ptr() + i * per * R * Cn * 2 * esz
+                    _lib.check(self.lib.jtb_lines_c2c_device(self.prec, self.dev, C.c_void_p(ptr), Cn, per * R, 1, 0, Cn,
+                                                             1, 0, 1.0, C.c_void_p(hp.cuda_stream)))
+                    self._evs[i].record(hp)
+                    main.wait_event(self._evs[i])
+                    _lib.check(self.lib.jtb_fft3d_k2_scatter_chunk(self.prec, self.dev, C.c_void_p(ptr), per,
+                                                                   self.rank * Ls + i * per, R, Cn, P, peers, 0,
+                                                                   C.c_void_p(main.cuda_stream)))
+            else:
+                _lib.check(self.lib.jtb_fft2d_slices_device(self.prec, self.dev, C.c_void_p(a.data_ptr()), Ls, R, Cn, P,
+                                                            self.rank, peers, 0, stream))
             if P == 1:
                 self._lines(a, S, R * Cn, R * Cn, 1, S * R * Cn, R * Cn)  # k1: across slices
                 return a
