@@ -233,6 +233,13 @@ def main():
         raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, world))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    try:
+        # pin this rank (and therefore its pinned host buffers, first-touch) to the CPUs next to its GPU
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+    except Exception:
+        pass
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.get()
@@ -348,6 +355,51 @@ def main():
                 "peak": hbm_peak, "peak_source": peak_kind, "unit": "GB/s", "frac": worst["GBps"] / hbm_peak,
                 "traffic": 4.238e9, "traffic_source": "profiles/r01_ncu_fft_fast_512_summary.json (ncu --set full, dram read+write per launch)",
                 "algorithmic_bytes_per_launch": 2 * local_bytes, "passes": per}
+    elif w.name == "fft3d_512" and world > 1 and slab.exchange == "p2p":
+        # per-kernel timing of the sharded step: local k3 pass, fused k2 pass + exchange (peer stores), k1 pass
+        S, R, Cn = w.dims
+        Ls, Rh = S // world, R // world
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+        def timed(fn, reps=5):
+            fn()
+            barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(reps):
+                fn()
+            ev1.record()
+            barrier()
+            t = torch.tensor([ev0.elapsed_time(ev1) / reps], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        def do_scatter():
+            slab.step += 1
+            _lib.check(lib.jtb_fft3d_k2_scatter(prec, local, C.c_void_p(a.data_ptr()), Ls, R, Cn, world, rank,
+                                                slab._peer["arr"][slab.step & 1], 0, st))
+            _lib.check(lib.jtb_peer_barrier(local, slab._peer["arr"][2], world, rank, slab.step, st))
+        recv = slab._recv_tensor(0)
+        t_k3 = timed(lambda: slab._lines(a, Cn, Ls * R, 1, 0, Cn, 1))
+        t_sc = timed(do_scatter)
+        t_k1 = timed(lambda: slab._lines(recv, S, Rh * Cn, Rh * Cn, 1, S * Rh * Cn, Rh * Cn))
+        nv_bytes = (world - 1) / world * local_bytes            # sent per GPU over NVLink
+        nv_peak = 770.0                                          # measured peer-copy GB/s per direction (B200_PROFILING.md)
+        per = [{"pass": "k3 rows (local)", "ms": t_k3, "GBps": 2 * local_bytes / (t_k3 * 1e-3) / 1e9},
+               {"pass": "k2 columns + exchange (peer stores) + barrier", "ms": t_sc,
+                "nvlink_GBps": nv_bytes / (t_sc * 1e-3) / 1e9, "hbm_GBps": 2 * local_bytes / (t_sc * 1e-3) / 1e9},
+               {"pass": "k1 slices (local, re-slabbed)", "ms": t_k1, "GBps": 2 * local_bytes / (t_k1 * 1e-3) / 1e9}]
+        model_ms = (6 * local_bytes / (hbm_peak * 1e9) + nv_bytes / 900e9) * 1e3
+        worst = max((per[0], per[2]), key=lambda p: p["ms"])
+        roof = {"bound": "hbm", "kernel": "fft_fast_kernel<double,512> " + worst["pass"], "achieved": worst["GBps"],
+                "peak": hbm_peak, "peak_source": peak_kind, "unit": "GB/s", "frac": worst["GBps"] / hbm_peak,
+                "traffic": None, "algorithmic_bytes_per_launch": 2 * local_bytes, "passes": per,
+                "nvlink": {"kernel": "fft_scatter_kernel<double,512> (k2 pass fused with the all-to-all)",
+                           "achieved": nv_bytes / (t_sc * 1e-3) / 1e9, "peak": nv_peak,
+                           "peak_source": "measured peer copy, B200_PROFILING.md (900 nominal)", "unit": "GB/s",
+                           "frac": nv_bytes / (t_sc * 1e-3) / 1e9 / nv_peak, "bytes_sent_per_gpu": nv_bytes},
+                "model_ms": model_ms, "frac_of_model": model_ms / ms_per_step,
+                "model": "BASELINE.md section 2: 6D/P / HBM peak + (P-1)/P * D/P / 900 GB/s, no overlap"}
     else:
         # whole-step model: `sweeps` read+write passes over the working set
         algo = 2.0 * w.sweeps * local_bytes

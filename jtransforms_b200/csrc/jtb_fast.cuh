@@ -33,11 +33,18 @@ template <typename S> struct FastTw {
 };
 
 template <typename T, typename S, bool STRIDED, int W> struct FastAddr {
+  // Bank-conflict rules (32 banks x 4 B; a 16-byte access is served per quarter warp, an 8-byte one per half warp):
+  //  * contiguous layout [w][i]: one pad element every 2^PADSH elements.  double2: PADSH = log2(E) (a quarter warp
+  //    never straddles a pad); float2: at least 4, otherwise 16 consecutive elements cross a pad and collide.
+  //  * line-interleaved layout [i][w]: W*sizeof(complex) >= 128 B needs no padding; 64-byte rows (float2, W = 8)
+  //    get one row of padding every 8 rows so that rows i and i+8 (stage-0 scatter) fall in different halves.
+  static constexpr int PADSH = (sizeof(T) == 4 && S::LOGPAD < 4) ? 4 : S::LOGPAD;
+  static constexpr bool ROWPAD = STRIDED && (W * 2 * sizeof(T) < 128);
   static constexpr int LD = STRIDED ? S::N : S::LD;
-  static constexpr int TILE = STRIDED ? S::N * W : S::LD * W;
+  static constexpr int TILE = STRIDED ? (ROWPAD ? S::N * W + (S::N >> 3) * W + W : S::N * W) : S::LD * W;
   __device__ static __forceinline__ int at(int i, int w) {
-    if (STRIDED) return i * W + w;
-    return w * S::LD + i + (i >> S::LOGPAD);
+    if (STRIDED) return ROWPAD ? (i + (i >> 3)) * W + w : i * W + w;
+    return w * S::LD + i + (i >> PADSH);
   }
 };
 

@@ -215,3 +215,10 @@ def test_fast2_r2r_strips_and_float(jt, monkeypatch):
 def test_fast_bluestein(jt):
     pc.fft1d_complex(jt, "Double", 140001)
     pc.fft1d_batch(jt, "Float", 131073, 2, pad=2)
+
+
+@pytest.mark.parametrize("prec,dims", [("Double", (256, 16)), ("Double", (128, 32)), ("Float", (256, 32)),
+                                       ("Float", (128, 64)), ("Float", (64, 64)), ("Double", (16, 256)),
+                                       ("Float", (32, 128))])
+def test_fast_kernel_small_sizes(jt, prec, dims):
+    pc.fftnd_complex(jt, prec, dims)
