@@ -12,7 +12,7 @@ template <typename T> struct FastEntry {
   int logn, loge, strided, W, threads, smem, twcount, nstages;
   int bits[JTB_MAX_STAGES];
   void (*kern)(const FastParams<T>);
-  bool attr_done;
+  unsigned attr_done;   // bit d set: smem attribute applied on device d
 };
 
 template <typename T, int LOGN, int LOGE, bool STRIDED, int W> FastEntry<T> make_entry() {
@@ -24,7 +24,7 @@ template <typename T, int LOGN, int LOGE, bool STRIDED, int W> FastEntry<T> make
   e.nstages = S::S;
   for (int s = 0; s < JTB_MAX_STAGES; ++s) e.bits[s] = s < S::S ? S::bits(s) : 0;
   e.kern = fft_fast_kernel<T, LOGN, LOGE, STRIDED, W>;
-  e.attr_done = false;
+  e.attr_done = 0;
   return e;
 }
 
@@ -116,16 +116,27 @@ int fast_c2c(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, int logn, bool in
     break;
   }
   if (!pick) return ST_OK;
-  if (!pick->attr_done) {
+  if (!(pick->attr_done & (1u << (e.ctx->device & 31)))) {
     JTB_CUDA(cudaFuncSetAttribute(pick->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pick->smem));
-    pick->attr_done = true;
+    pick->attr_done |= 1u << (e.ctx->device & 31);
   }
   FastParams<T> p;
   p.a = a; p.nlines = nlines;
   p.line_dist = g.d[3]; p.c0 = (int)g.c[0]; p.stride = (int)g.stride;
   p.inverse = inverse; p.has_scale = has_scale; p.scale = scale;
   JTB_TRY(fast_stage_table<T>(e, pick->logn, pick->loge, &p.twg));
-  const i64 nblk = (nlines + pick->W - 1) / pick->W;
+  p.reps = 1;
+  if (strided) {
+    // lines whose elements are >= 2 MB apart touch one TLB page per element: let a CTA reuse its translations for a
+    // few neighbouring column groups (JTB_FAST_REPS overrides)
+    const char* er = getenv("JTB_FAST_REPS");
+    const i64 bytes_stride = g.stride * (i64)sizeof(cx<T>);
+    p.reps = er ? atoi(er) : 1;   // measured: no gain from 2..8 on the 4 MiB-stride pass
+    (void)bytes_stride;
+    if (p.reps < 1) p.reps = 1;
+    while (p.reps > 1 && ((g.c[0] / pick->W) % p.reps) != 0) --p.reps;
+  }
+  const i64 nblk = ((nlines + pick->W - 1) / pick->W + p.reps - 1) / p.reps;
   if (nblk > 0x7fffffffLL) return ST_OK;
   JTB_LAUNCH(pick->kern, (unsigned)nblk, (unsigned)pick->threads, (size_t)pick->smem, e.st, p);
   JTB_CUDA(cudaGetLastError());
@@ -139,7 +150,7 @@ namespace {
 template <typename T> struct ScatterEntry {
   int logn, W, threads, smem, loge;
   void (*kern)(const ScatterParams<T>);
-  bool attr_done;
+  unsigned attr_done;   // bit d set: smem attribute applied on device d
 };
 template <typename T, int LOGN, int LOGE, int W> ScatterEntry<T> make_scatter() {
   typedef Sched<LOGN, LOGE> S;
@@ -147,7 +158,7 @@ template <typename T, int LOGN, int LOGE, int W> ScatterEntry<T> make_scatter() 
   e.logn = LOGN; e.loge = LOGE; e.W = W; e.threads = W * S::TPL;
   e.smem = (int)((FastAddr<T, S, true, W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
   e.kern = fft_scatter_kernel<T, LOGN, LOGE, W>;
-  e.attr_done = false;
+  e.attr_done = 0;
   return e;
 }
 template <typename T> std::vector<ScatterEntry<T>>& scatter_registry();
@@ -175,9 +186,9 @@ int fast_scatter(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, int nranks
     if (f.logn == logn && Cn % f.W == 0) { pick = &f; break; }
   if (!pick) { set_error("no fused-exchange kernel for %lld rows x %lld columns", (long long)R, (long long)Cn); return ST_UNSUPPORTED; }
   if (Ls * (Cn / pick->W) > 0x7fffffffLL || Ls * R * Cn >= (1LL << 40)) { set_error("slab too large"); return ST_UNSUPPORTED; }
-  if (!pick->attr_done) {
+  if (!(pick->attr_done & (1u << (e.ctx->device & 31)))) {
     JTB_CUDA(cudaFuncSetAttribute(pick->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pick->smem));
-    pick->attr_done = true;
+    pick->attr_done |= 1u << (e.ctx->device & 31);
   }
   ScatterParams<T> p;
   p.a = a;

@@ -24,6 +24,7 @@ template <typename T> struct FastParams {
   int has_scale;
   T scale;
   const cx<T>* twg;  // base twiddles, layout below (fast_twiddle_count entries)
+  int reps;          // strided layout: consecutive groups of W lines handled by one CTA (TLB / launch amortisation)
 };
 
 // base twiddle table: for stage s >= 1 and j < bits(s):  tab[toff(s) + j*ns(s) + k] = exp(-2 pi i 2^j k / (ns(s) 2^bits(s)))
@@ -127,44 +128,48 @@ fft_fast_kernel(const FastParams<T> p) {
   if (STRIDED) { w = tid % W; t = tid / W; } else { t = tid % S::TPL; w = tid / S::TPL; }
   for (int i = tid; i < FastTw<S>::COUNT; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
 
-  const i64 line0 = (i64)blockIdx.x * W;
-  C* base;
-  int es;
-  bool valid = true;
-  if (STRIDED) {
-    const i64 grp = line0 / p.c0;
-    const int c = (int)(line0 - grp * p.c0);
-    base = p.a + grp * p.line_dist + c + w;
-    es = p.stride;
-  } else {
-    valid = line0 + w < p.nlines;
-    base = p.a + (valid ? (line0 + w) * p.line_dist : 0);
-    es = 1;
-  }
-  C v[S::E];
-  if (valid) {
+  for (int rep = 0; rep < (STRIDED ? p.reps : 1); ++rep) {
+    const i64 line0 = ((i64)blockIdx.x * (STRIDED ? p.reps : 1) + rep) * W;
+    if (line0 >= p.nlines) break;
+    C* base;
+    int es;
+    bool valid = true;
+    if (STRIDED) {
+      const i64 grp = line0 / p.c0;
+      const int c = (int)(line0 - grp * p.c0);
+      base = p.a + grp * p.line_dist + c + w;
+      es = p.stride;
+    } else {
+      valid = line0 + w < p.nlines;
+      base = p.a + (valid ? (line0 + w) * p.line_dist : 0);
+      es = 1;
+    }
+    C v[S::E];
+    if (valid) {
 #pragma unroll
-    for (int q = 0; q < S::E; ++q) v[q] = base[(t + q * S::TPL) * es];
-  } else {
+      for (int q = 0; q < S::E; ++q) v[q] = base[(t + q * S::TPL) * es];
+    } else {
 #pragma unroll
-    for (int q = 0; q < S::E; ++q) v[q] = mk<T>(0, 0);
-  }
-  if (p.inverse) {
+      for (int q = 0; q < S::E; ++q) v[q] = mk<T>(0, 0);
+    }
+    if (p.inverse) {
 #pragma unroll
-    for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
-  }
-  FastLoop<T, S, 0, STRIDED, W>::run(v, sm, twt, t, w);
-  if (p.has_scale) {
+      for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
+    }
+    if (rep > 0) __syncthreads();      // the previous group's last shared-memory reads are done
+    FastLoop<T, S, 0, STRIDED, W>::run(v, sm, twt, t, w);
+    if (p.has_scale) {
 #pragma unroll
-    for (int q = 0; q < S::E; ++q) { v[q].x *= p.scale; v[q].y *= p.scale; }
-  }
-  if (p.inverse) {
+      for (int q = 0; q < S::E; ++q) { v[q].x *= p.scale; v[q].y *= p.scale; }
+    }
+    if (p.inverse) {
 #pragma unroll
-    for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
-  }
-  if (valid) {
+      for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
+    }
+    if (valid) {
 #pragma unroll
-    for (int q = 0; q < S::E; ++q) base[(t + q * S::TPL) * es] = v[q];
+      for (int q = 0; q < S::E; ++q) base[(t + q * S::TPL) * es] = v[q];
+    }
   }
 }
 

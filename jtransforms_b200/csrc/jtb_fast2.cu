@@ -13,7 +13,7 @@ namespace {
 template <typename T> struct F2Entry {
   int logn, loge, sin, mode, W, threads, smem;
   void (*kern)(const Fast2Params<T>);
-  bool attr_done;
+  unsigned attr_done;   // bit d set: smem attribute applied on device d
   i64 min_lines;             // use this variant only for launches with at least this many lines (grid fill)
   const cx<T>* twg[16];      // per-device base twiddle table
 };
@@ -23,7 +23,7 @@ template <typename T, int LOGN, int LOGE, bool SIN, int MODE, int W> F2Entry<T> 
   e.logn = LOGN; e.loge = LOGE; e.sin = SIN; e.mode = MODE; e.W = W; e.threads = W * S::TPL;
   e.smem = (int)((FastAddr<T, S, SIN, W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
   e.kern = fft_fast2_kernel<T, LOGN, LOGE, SIN, MODE, W>;
-  e.attr_done = false;
+  e.attr_done = 0;
   e.min_lines = min_lines;
   for (int d = 0; d < 16; ++d) e.twg[d] = nullptr;
   return e;
@@ -63,9 +63,9 @@ template <typename T> F2Entry<T>* find2(int logn, bool sin, int mode, i64 lines 
 }
 
 template <typename T> int launch2(Engine<T>& e, F2Entry<T>* f, Fast2Params<T>& p) {
-  if (!f->attr_done) {
+  if (!(f->attr_done & (1u << (e.ctx->device & 31)))) {
     JTB_CUDA(cudaFuncSetAttribute(f->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, f->smem));
-    f->attr_done = true;
+    f->attr_done |= 1u << (e.ctx->device & 31);
   }
   const int dv = e.ctx->device & 15;
   if (!f->twg[dv]) JTB_TRY(fast_stage_table<T>(e, f->logn, f->loge, &f->twg[dv]));
@@ -225,7 +225,7 @@ namespace {
 template <typename T> struct RowEntry {
   int logn, loge, kind, W, threads, smem;
   void (*kern)(const RowR2RParams<T>);
-  bool attr_done;
+  unsigned attr_done;   // bit d set: smem attribute applied on device d
 };
 template <typename T, int LOGN, int LOGE, int KIND, int W> RowEntry<T> mkrow() {
   typedef Sched<LOGN, LOGE> S;
@@ -233,7 +233,7 @@ template <typename T, int LOGN, int LOGE, int KIND, int W> RowEntry<T> mkrow() {
   e.logn = LOGN; e.loge = LOGE; e.kind = KIND; e.W = W; e.threads = W * S::TPL;
   e.smem = (int)((FastAddr<T, S, false, W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
   e.kern = fft_r2r_row_kernel<T, LOGN, LOGE, KIND, W>;
-  e.attr_done = false;
+  e.attr_done = 0;
   return e;
 }
 #define JTB_ROWS(T, LOGN, LOGE, W) mkrow<T, LOGN, LOGE, RK_DCT, W>(), mkrow<T, LOGN, LOGE, RK_DST, W>(), mkrow<T, LOGN, LOGE, RK_DHT, W>()
@@ -258,7 +258,7 @@ template <typename T, int LOGN, int LOGE, int W, int PRE> PreEntry<T> mkpre() {
   e.logn = LOGN; e.loge = LOGE; e.sin = 1; e.mode = FM_TWID; e.W = W; e.threads = W * S::TPL;
   e.smem = (int)((FastAddr<T, S, true, W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
   e.kern = fft_fast2_kernel<T, LOGN, LOGE, true, FM_TWID, W, PRE>;
-  e.attr_done = false; e.min_lines = 0;
+  e.attr_done = 0; e.min_lines = 0;
   for (int d = 0; d < 16; ++d) e.twg[d] = nullptr;
   return x;
 }
@@ -278,7 +278,7 @@ namespace {
 template <typename T> struct PairEntry {
   int logn, loge, W, threads, smem;
   void (*kern)(const ColPairParams<T>);
-  bool attr_done;
+  unsigned attr_done;   // bit d set: smem attribute applied on device d
 };
 template <typename T, int LOGN, int LOGE, int W> PairEntry<T> mkpair() {
   typedef Sched<LOGN, LOGE> S;
@@ -286,7 +286,7 @@ template <typename T, int LOGN, int LOGE, int W> PairEntry<T> mkpair() {
   e.logn = LOGN; e.loge = LOGE; e.W = W; e.threads = 2 * W * S::TPL;
   e.smem = (int)((FastAddr<T, S, true, 2 * W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
   e.kern = fft_colpair_kernel<T, LOGN, LOGE, W>;
-  e.attr_done = false;
+  e.attr_done = 0;
   return e;
 }
 template <typename T> std::vector<PairEntry<T>>& pairreg();
@@ -310,9 +310,9 @@ int fast_r2r_rows(Engine<T>& e, T* a, i64 dist, i64 nlines, i64 n, int kind, T f
   RowEntry<T>* r = nullptr;
   for (auto& x : rowreg<T>()) if (x.logn == logN && x.kind == kind) { r = &x; break; }
   if (!r) return ST_OK;
-  if (!r->attr_done) {
+  if (!(r->attr_done & (1u << (e.ctx->device & 31)))) {
     JTB_CUDA(cudaFuncSetAttribute(r->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, r->smem));
-    r->attr_done = true;
+    r->attr_done |= 1u << (e.ctx->device & 31);
   }
   RowR2RParams<T> p;
   p.a = a; p.nlines = nlines; p.dist = dist; p.f0 = f0; p.f = f;
@@ -382,9 +382,9 @@ int fast_r2r_cols(Engine<T>& e, T* a, i64 n, i64 Cn, i64 batches, i64 bdist, int
     JTB_TRY(launch2(e, f1, p));
     if (fp) {
       // second pass + pair post-pass in one kernel, writing the final result
-      if (!fp->attr_done) {
+      if (!(fp->attr_done & (1u << (e.ctx->device & 31)))) {
         JTB_CUDA(cudaFuncSetAttribute(fp->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fp->smem));
-        fp->attr_done = true;
+        fp->attr_done |= 1u << (e.ctx->device & 31);
       }
       ColPairParams<T> cp;
       cp.z = wk + cs; cp.out = ac + cs; cp.s = s; cp.bdist = bd;
@@ -426,14 +426,14 @@ template <typename T, int LOGN, int LOGE, int W, int MODE, int PRE> F2Entry<T> m
   e.logn = LOGN; e.loge = LOGE; e.sin = 1; e.mode = MODE; e.W = W; e.threads = W * S::TPL;
   e.smem = (int)((FastAddr<T, S, true, W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
   e.kern = fft_fast2_kernel<T, LOGN, LOGE, true, MODE, W, PRE>;
-  e.attr_done = false; e.min_lines = 0;
+  e.attr_done = 0; e.min_lines = 0;
   for (int d = 0; d < 16; ++d) e.twg[d] = nullptr;
   return e;
 }
 template <typename T> struct ConvEntry {
   int logn, loge, W, threads, smem;
   void (*kern)(const ConvParams<T>);
-  bool attr_done;
+  unsigned attr_done;   // bit d set: smem attribute applied on device d
 };
 template <typename T, int LOGN, int LOGE, int W> ConvEntry<T> mkconv() {
   typedef Sched<LOGN, LOGE> S;
@@ -441,7 +441,7 @@ template <typename T, int LOGN, int LOGE, int W> ConvEntry<T> mkconv() {
   e.logn = LOGN; e.loge = LOGE; e.W = W; e.threads = W * S::TPL;
   e.smem = (int)((FastAddr<T, S, false, W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
   e.kern = fft_conv_kernel<T, LOGN, LOGE, W>;
-  e.attr_done = false;
+  e.attr_done = 0;
   return e;
 }
 template <typename T> struct BlueReg {
@@ -516,9 +516,9 @@ int fast_bluestein_contig(Engine<T>& e, cx<T>* a, i64 dist, i64 nlines, i64 n, b
   if (chunk > nlines) chunk = nlines;
   JTB_TRY(e.ctx->ensure(e.ctx->work[WK_BLUE], (size_t)chunk * (size_t)M * sizeof(C)));
   C* wk = (C*)e.ctx->work[WK_BLUE].p;
-  if (!fb->attr_done) {
+  if (!(fb->attr_done & (1u << (e.ctx->device & 31)))) {
     JTB_CUDA(cudaFuncSetAttribute(fb->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fb->smem));
-    fb->attr_done = true;
+    fb->attr_done |= 1u << (e.ctx->device & 31);
   }
   const cx<T>* twb;
   JTB_TRY(fast_stage_table<T>(e, fb->logn, fb->loge, &twb));

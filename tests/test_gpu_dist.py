@@ -28,3 +28,26 @@ def test_slab_two_gpus():
            "127.0.0.1", "--master-port", "29631", os.path.join(HERE, "dist_gpu_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_plans_on_two_devices_in_one_process():
+    """per-device state (tables, shared-memory attributes, streams) must not leak between devices"""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import jtransforms_b200 as jt
+    from oracle import jt_oracle as o
+    for dims in [(64, 512, 64), (8, 1024, 16)]:
+        S, R, Cn = dims
+        x = o.fill_uniform(2 * S * R * Cn, seed=9)
+        want = o.complex_forward_3d(x, S, R, Cn)
+        for dev in (0, 1, 0):
+            a = x.copy()
+            jt.DoubleFFT_3D(S, R, Cn, device=dev).complexForward(a)
+            assert o.rel_l2(a, want) < 1e-12 * 24
+    y = o.fill_uniform(8192, seed=1)
+    for dev in (1, 0):
+        b = y.copy()
+        jt.DoubleDCT_1D(8192, device=dev).forward(b, True)
+        assert o.rel_l2(b, o.dct_forward_nd(y, (8192,), True)) < 1e-12 * 13
