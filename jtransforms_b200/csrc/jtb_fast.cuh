@@ -28,9 +28,16 @@ template <typename T> struct FastParams {
 };
 
 // base twiddle table: for stage s >= 1 and j < bits(s):  tab[toff(s) + j*ns(s) + k] = exp(-2 pi i 2^j k / (ns(s) 2^bits(s)))
+// Only the tables of the early stages (few entries, every entry reused by many threads of the CTA) are staged in
+// shared memory; a late stage with ns(s)*bits(s) > SM_LIMIT entries has (almost) no reuse inside one CTA, so its
+// twiddles are read straight from global memory (coalesced, L1/L2 resident) instead of being copied per CTA.
 template <typename S> struct FastTw {
+  static constexpr int SM_LIMIT = 768;
   __host__ __device__ static constexpr int toff(int s) { int o = 0; for (int i = 1; i < s; ++i) o += S::bits(i) * S::ns(i); return o; }
+  __host__ __device__ static constexpr bool in_smem(int s) { return S::bits(s) * S::ns(s) <= SM_LIMIT; }
+  __host__ __device__ static constexpr int sm_count() { int o = 0; for (int i = 1; i < S::S; ++i) if (in_smem(i)) o = toff(i + 1); return o; }
   static constexpr int COUNT = toff(S::S);
+  static constexpr int COUNT_SM = sm_count();
 };
 
 template <typename T, typename S, bool STRIDED, int W> struct FastAddr {
@@ -56,7 +63,7 @@ template <typename T, typename S, int s, bool STRIDED, int W> struct FastStage {
   static constexpr int NS = S::ns(s);
   typedef FastAddr<T, S, STRIDED, W> A;
 
-  __device__ static __forceinline__ void compute(cx<T>* v, int t, const cx<T>* twt) {
+  __device__ static __forceinline__ void compute(cx<T>* v, int t, const cx<T>* twt, const cx<T>* __restrict__ twg) {
 #pragma unroll
     for (int m = 0; m < NB; ++m) {
       cx<T> x[R];
@@ -67,7 +74,8 @@ template <typename T, typename S, int s, bool STRIDED, int W> struct FastStage {
         constexpr int TOFF = FastTw<S>::toff(s);
         cx<T> tw[R];
 #pragma unroll
-        for (int j = 0; j < LOGR; ++j) tw[1 << j] = twt[TOFF + j * NS + k];
+        for (int j = 0; j < LOGR; ++j)
+          tw[1 << j] = FastTw<S>::in_smem(s) ? twt[TOFF + j * NS + k] : __ldg(twg + TOFF + j * NS + k);
 #pragma unroll
         for (int r = 3; r < R; ++r) {
           // highest set bit h of r; r = 2^h + rest
@@ -96,15 +104,15 @@ template <typename T, typename S, int s, bool STRIDED, int W> struct FastStage {
 
 template <typename T, typename S, int s, bool STRIDED, int W> struct FastLoop {
   typedef FastAddr<T, S, STRIDED, W> A;
-  __device__ static __forceinline__ void run(cx<T>* v, cx<T>* sm, const cx<T>* twt, int t, int w) {
-    FastStage<T, S, s, STRIDED, W>::compute(v, t, twt);
+  __device__ static __forceinline__ void run(cx<T>* v, cx<T>* sm, const cx<T>* twt, int t, int w, const cx<T>* twg) {
+    FastStage<T, S, s, STRIDED, W>::compute(v, t, twt, twg);
     if (s + 1 < S::S) {
       if (s > 0) __syncthreads();
       FastStage<T, S, s, STRIDED, W>::scatter(v, sm, t, w);
       __syncthreads();
 #pragma unroll
       for (int q = 0; q < S::E; ++q) v[q] = sm[A::at(t + q * S::TPL, w)];
-      FastLoop<T, S, (s + 1 < S::S ? s + 1 : s), STRIDED, W>::run(v, sm, twt, t, w);
+      FastLoop<T, S, (s + 1 < S::S ? s + 1 : s), STRIDED, W>::run(v, sm, twt, t, w, twg);
     }
   }
 };
@@ -126,7 +134,7 @@ fft_fast_kernel(const FastParams<T> p) {
   const int tid = threadIdx.x;
   int w, t;
   if (STRIDED) { w = tid % W; t = tid / W; } else { t = tid % S::TPL; w = tid / S::TPL; }
-  for (int i = tid; i < FastTw<S>::COUNT; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
+  for (int i = tid; i < FastTw<S>::COUNT_SM; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
 
   for (int rep = 0; rep < (STRIDED ? p.reps : 1); ++rep) {
     const i64 line0 = ((i64)blockIdx.x * (STRIDED ? p.reps : 1) + rep) * W;
@@ -157,7 +165,7 @@ fft_fast_kernel(const FastParams<T> p) {
       for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
     }
     if (rep > 0) __syncthreads();      // the previous group's last shared-memory reads are done
-    FastLoop<T, S, 0, STRIDED, W>::run(v, sm, twt, t, w);
+    FastLoop<T, S, 0, STRIDED, W>::run(v, sm, twt, t, w, p.twg);
     if (p.has_scale) {
 #pragma unroll
       for (int q = 0; q < S::E; ++q) { v[q].x *= p.scale; v[q].y *= p.scale; }
@@ -201,7 +209,7 @@ fft_scatter_kernel(const ScatterParams<T> p) {
   C* twt = sm + A::TILE;
   const int tid = threadIdx.x;
   const int w = tid % W, t = tid / W;
-  for (int i = tid; i < FastTw<S>::COUNT; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
+  for (int i = tid; i < FastTw<S>::COUNT_SM; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
   const int groups = p.C / W;                       // column groups per slice
   const int ls = blockIdx.x / groups;
   const int c = (blockIdx.x - ls * groups) * W + w;
@@ -213,7 +221,7 @@ fft_scatter_kernel(const ScatterParams<T> p) {
 #pragma unroll
     for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
   }
-  FastLoop<T, S, 0, true, W>::run(v, sm, twt, t, w);
+  FastLoop<T, S, 0, true, W>::run(v, sm, twt, t, w, p.twg);
   if (p.inverse) {
 #pragma unroll
     for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
@@ -261,7 +269,7 @@ __global__ void __launch_bounds__(W * Sched<LOGN, LOGE>::TPL, 2) fft_slice2d_ker
   C* sm = reinterpret_cast<C*>(smem_raw);
   C* twt = sm + (AC::TILE > AS::TILE ? AC::TILE : AS::TILE);
   const int tid = threadIdx.x;
-  for (int i = tid; i < FastTw<S>::COUNT; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
+  for (int i = tid; i < FastTw<S>::COUNT_SM; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
   const int nteams = gridDim.x / p.team;
   const int team = blockIdx.x / p.team, rank = blockIdx.x - team * p.team;
   if (team >= nteams) return;
@@ -280,7 +288,7 @@ __global__ void __launch_bounds__(W * Sched<LOGN, LOGE>::TPL, 2) fft_slice2d_ker
 #pragma unroll
           for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
         }
-        FastLoop<T, S, 0, false, W>::run(v, sm, twt, t, w);
+        FastLoop<T, S, 0, false, W>::run(v, sm, twt, t, w, p.twg);
 #pragma unroll
         for (int q = 0; q < S::E; ++q) base[t + q * S::TPL] = v[q];   // stays in the swapped domain for phase B
         __syncthreads();
@@ -304,7 +312,7 @@ __global__ void __launch_bounds__(W * Sched<LOGN, LOGE>::TPL, 2) fft_slice2d_ker
         const C* base = sl + c0 + w;
 #pragma unroll
         for (int q = 0; q < S::E; ++q) v[q] = __ldcg(base + (i64)(t + q * S::TPL) * N);
-        FastLoop<T, S, 0, true, W>::run(v, sm, twt, t, w);
+        FastLoop<T, S, 0, true, W>::run(v, sm, twt, t, w, p.twg);
         if (p.has_scale) {
 #pragma unroll
           for (int q = 0; q < S::E; ++q) { v[q].x *= p.scale; v[q].y *= p.scale; }

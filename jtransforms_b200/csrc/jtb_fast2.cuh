@@ -62,7 +62,7 @@ fft_fast2_kernel(const Fast2Params<T> p) {
   const int tid = threadIdx.x;
   int w, t;
   if (SIN) { w = tid % W; t = tid / W; } else { t = tid % S::TPL; w = tid / S::TPL; }
-  for (int i = tid; i < FastTw<S>::COUNT; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
+  for (int i = tid; i < FastTw<S>::COUNT_SM; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
 
   const i64 line0 = (i64)blockIdx.x * W;
   const i64 line = line0 + w;
@@ -108,7 +108,7 @@ fft_fast2_kernel(const Fast2Params<T> p) {
 #pragma unroll
     for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
   }
-  FastLoop<T, S, 0, SIN, W>::run(v, sm, twt, t, w);
+  FastLoop<T, S, 0, SIN, W>::run(v, sm, twt, t, w, p.twg);
   if (MODE == FM_CHIRP_OUT) {
     if (valid) {
       C* dst = p.out + g_lo * p.out_gdist + g_hi * p.out_gdist2;
@@ -234,7 +234,7 @@ fft_conv_kernel(const ConvParams<T> p) {
   C* twt = sm + A::TILE;
   const int tid = threadIdx.x;
   const int t = tid % S::TPL, w = tid / S::TPL;
-  for (int i = tid; i < FastTw<S>::COUNT; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
+  for (int i = tid; i < FastTw<S>::COUNT_SM; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
   const i64 line = (i64)blockIdx.x * W + w;
   const bool valid = line < p.nlines;
   const int k1 = (int)(line % p.N1);
@@ -247,14 +247,14 @@ fft_conv_kernel(const ConvParams<T> p) {
 #pragma unroll
     for (int q = 0; q < S::E; ++q) v[q] = mk<T>(0, 0);
   }
-  FastLoop<T, S, 0, false, W>::run(v, sm, twt, t, w);
+  FastLoop<T, S, 0, false, W>::run(v, sm, twt, t, w, p.twg);
   if (valid) {
     const C* h = p.h + (i64)k1 * S::N;
 #pragma unroll
     for (int q = 0; q < S::E; ++q) v[q] = cswap(cmul(v[q], __ldg(h + t + q * S::TPL)));
   }
   if (S::S > 1) __syncthreads();
-  FastLoop<T, S, 0, false, W>::run(v, sm, twt, t, w);
+  FastLoop<T, S, 0, false, W>::run(v, sm, twt, t, w, p.twg);
   if (valid) {
     // conj(W_M^(k1*m2)), m2 = t + q*TPL, as a chain  conj(W^(k1 t)) * conj(W^(k1 TPL))^q
     const int L = (1 << p.fs_logL) - 1;
@@ -300,7 +300,7 @@ fft_r2r_row_kernel(const RowR2RParams<T> p) {
   C* twt = sm + A::TILE;
   const int tid = threadIdx.x;
   const int t = tid % S::TPL, w = tid / S::TPL;
-  for (int i = tid; i < FastTw<S>::COUNT; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
+  for (int i = tid; i < FastTw<S>::COUNT_SM; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
   const i64 line0 = (i64)blockIdx.x * W;
   const int nl = (p.nlines - line0 < W) ? (int)(p.nlines - line0) : W;
   const bool valid = w < nl;
@@ -333,7 +333,7 @@ fft_r2r_row_kernel(const RowR2RParams<T> p) {
     for (int q = 0; q < S::E; ++q) v[q] = mk<T>(0, 0);
   }
   __syncthreads();
-  FastLoop<T, S, 0, false, W>::run(v, sm, twt, t, w);
+  FastLoop<T, S, 0, false, W>::run(v, sm, twt, t, w, p.twg);
   if (S::S > 1) __syncthreads();
 #pragma unroll
   for (int q = 0; q < S::E; ++q) sm[A::at(t + q * S::TPL, w)] = v[q];
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(2 * W * Sched<LOGN, LOGE>::TPL, 2) fft_colpair
   const int tid = threadIdx.x;
   const int wu = tid % W2, t = tid / W2;          // wu = u*W + w
   const int u = wu / W, w = wu - u * W;
-  for (int i = tid; i < FastTw<S>::COUNT; i += W2 * S::TPL) twt[i] = __ldg(p.twg + i);
+  for (int i = tid; i < FastTw<S>::COUNT_SM; i += W2 * S::TPL) twt[i] = __ldg(p.twg + i);
   // block -> (column group, line pair, batch)
   const int groups = p.cols / W, pairs = p.R1 / 2 + 1;
   int b = blockIdx.x;
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(2 * W * Sched<LOGN, LOGE>::TPL, 2) fft_colpair
   C v[S::E];
 #pragma unroll
   for (int q = 0; q < S::E; ++q) v[q] = src[(i64)(t + q * S::TPL) * p.s];
-  FastLoop<T, S, 0, true, W2>::run(v, sm, twt, t, wu);
+  FastLoop<T, S, 0, true, W2>::run(v, sm, twt, t, wu, p.twg);
   if (S::S > 1) __syncthreads();
 #pragma unroll
   for (int q = 0; q < S::E; ++q) sm[A::at(t + q * S::TPL, wu)] = v[q];
