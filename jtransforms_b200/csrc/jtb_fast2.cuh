@@ -308,17 +308,24 @@ fft_r2r_row_kernel(const RowR2RParams<T> p) {
   // v[n-1-u] = x[2u+1]; DST additionally negates the odd samples) so that the gather below is one conflict-free
   // 16-byte read per element: z[j] = (v[2j], v[2j+1])
   {
+    // W*N complex loads by W*TPL threads = exactly E per thread: all issued before the first is consumed
     const C* src = reinterpret_cast<const C*>(p.a);
-    for (int idx = tid; idx < W * N; idx += W * S::TPL) {
+    C xr[S::E];
+#pragma unroll
+    for (int it = 0; it < S::E; ++it) {
+      const int idx = tid + it * (W * S::TPL);
       const int ww = idx / N, u = idx - ww * N;
-      if (ww < nl) {
-        const C xv = src[((line0 + ww) * p.dist) / 2 + u];
-        if (KIND == RK_DHT) reinterpret_cast<C*>(smr)[ww * N + u] = xv;
-        else {
-          T* vs = smr + ww * n;
-          vs[u] = xv.x;
-          vs[n - 1 - u] = (KIND == RK_DST) ? -xv.y : xv.y;
-        }
+      xr[it] = (ww < nl) ? src[((line0 + ww) * p.dist) / 2 + u] : mk<T>(0, 0);
+    }
+#pragma unroll
+    for (int it = 0; it < S::E; ++it) {
+      const int idx = tid + it * (W * S::TPL);
+      const int ww = idx / N, u = idx - ww * N;
+      if (KIND == RK_DHT) reinterpret_cast<C*>(smr)[ww * N + u] = xr[it];
+      else {
+        T* vs = smr + ww * n;
+        vs[u] = xr[it].x;
+        vs[n - 1 - u] = (KIND == RK_DST) ? -xr[it].y : xr[it].y;
       }
     }
   }

@@ -162,3 +162,33 @@ def test_dct2d_8192(jt):
     jt.DoubleDCT_2D(n, n).forward(a, True)
     want = sfft.dctn(x.reshape(n, n), type=2, norm="ortho", workers=-1).ravel()
     pc.check(a, want, "Double", n * n, "DCT 8192^2")
+
+
+def test_large_64bit_indexing(jt):
+    """arrays beyond 2^31 bytes / 2^30 elements, device resident: 1024^3 complex double (16 GiB) round trip +
+    Parseval, and a 2^26-point 1-D transform against the oracle"""
+    import ctypes
+    import torch
+    lib = __import__("jtransforms_b200")._lib.get()
+    S = R = C = 1024
+    N = S * R * C
+    a = torch.empty(2 * N, dtype=torch.float64, device="cuda:0")
+    assert lib.jtb_fill_uniform_device(0, 0, ctypes.c_void_p(a.data_ptr()), 2 * N, 7, -1.0, 1.0, None) == 0
+    torch.cuda.synchronize()
+    e_in = float((a * a).sum())
+    probe = a[-4096:].clone()
+    f = jt.DoubleFFT_3D(S, R, C)
+    f.complexForward(a)
+    torch.cuda.synchronize()
+    e_out = float((a * a).sum())
+    assert abs(e_out / (N * e_in) - 1.0) < 1e-12
+    f.complexInverse(a, True)
+    torch.cuda.synchronize()
+    assert float(torch.linalg.norm(a[-4096:] - probe) / torch.linalg.norm(probe)) < 1e-12 * 30
+    del a
+    torch.cuda.empty_cache()
+    n = 1 << 26
+    x = o.fill_uniform(2 * n, seed=13, lo=-1.0, hi=1.0)
+    b = x.copy()
+    jt.DoubleFFT_1D(n).complexForward(b)
+    pc.check(b, o.complex_forward_1d(x, n), "Double", n, "2^26")
