@@ -47,7 +47,21 @@ class SlabFFT3D:
         import os as _os
         self.chunks = int(_os.environ.get("JTB_SLAB_CHUNKS", "1"))   # >1: pipeline k3 under the exchange (measured: no gain)
         if self.P > 1 and exchange == "p2p":
-            self._setup_p2p()
+            # every rank must take the same path: agree on success before committing to peer stores
+            ok = 1
+            try:
+                self._setup_p2p()
+            except Exception as e:       # no peer access / IPC on this box
+                ok = 0
+                self._p2p_error = repr(e)
+            flag = torch.tensor([ok], dtype=torch.int32, device=torch.device("cuda", self.dev))
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if int(flag.item()) == 0:
+                import warnings
+                warnings.warn("peer-mapped exchange unavailable (%s); using the NCCL all-to-all"
+                              % getattr(self, "_p2p_error", "a peer failed"))
+                self._peer = None
+                self.exchange = "nccl"
 
     # ---- peer-mapped receive buffers (double buffered) + barrier flags
     def _setup_p2p(self):
@@ -72,7 +86,7 @@ class SlabFFT3D:
                     ptrs[b][r] = q.value
         self._peer = {"mine": mine, "ptrs": ptrs, "nbytes": nbytes,
                       "arr": [(C.c_void_p * P)(*ptrs[b]) for b in range(3)]}
-        dist.barrier(group=self.group)
+        # (the caller's all_reduce is the barrier that makes every mapping visible before first use)
 
     def _recv_tensor(self, b: int) -> torch.Tensor:
         class _Wrap:
