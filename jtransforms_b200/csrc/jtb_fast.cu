@@ -41,6 +41,7 @@ template <> std::vector<FastEntry<double>>& registry<double>() {
       make_entry<double, 10, 4, true, 8>(), make_entry<double, 10, 4, true, 4>(),
       make_entry<double, 10, 4, false, 4>(), make_entry<double, 10, 4, false, 2>(),
       make_entry<double, 12, 4, false, 1>(), make_entry<double, 12, 4, false, 2>(),
+      make_entry<double, 13, 4, false, 1>(),
       make_entry<double, 8, 4, true, 8>(), make_entry<double, 8, 4, false, 8>(),
       make_entry<double, 7, 4, true, 16>(), make_entry<double, 7, 4, false, 16>(),
       make_entry<double, 11, 4, false, 2>(), make_entry<double, 11, 4, false, 4>(),
@@ -54,6 +55,7 @@ template <> std::vector<FastEntry<float>>& registry<float>() {
       make_entry<float, 10, 4, true, 16>(), make_entry<float, 10, 4, true, 8>(),
       make_entry<float, 10, 4, false, 4>(), make_entry<float, 10, 4, false, 2>(),
       make_entry<float, 11, 4, true, 8>(),
+      make_entry<float, 12, 4, false, 1>(), make_entry<float, 13, 4, false, 1>(),
       make_entry<float, 8, 4, true, 16>(), make_entry<float, 8, 4, false, 16>(),
       make_entry<float, 7, 4, true, 16>(), make_entry<float, 7, 4, false, 16>(),
       make_entry<float, 6, 3, true, 16>(), make_entry<float, 6, 3, false, 32>(),

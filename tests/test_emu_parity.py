@@ -222,3 +222,9 @@ def test_fast_bluestein(jt):
                                        ("Float", (32, 128))])
 def test_fast_kernel_small_sizes(jt, prec, dims):
     pc.fftnd_complex(jt, prec, dims)
+
+
+def test_fast_kernel_8192_rows(jt):
+    pc.fft1d_batch(jt, "Double", 8192, 2, pad=2)
+    pc.fft1d_batch(jt, "Float", 8192, 2)
+    pc.fft1d_complex(jt, "Float", 4096)
