@@ -29,7 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "fft_gflops_5NlogN"
+METRIC = "FFT GFLOP/s (5N*log2N/t)"
 UNIT = "GFLOP/s"
 
 
