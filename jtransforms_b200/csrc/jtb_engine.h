@@ -120,6 +120,9 @@ int fast_bluestein_contig(Engine<T>& e, cx<T>* a, i64 dist, i64 nlines, i64 n, b
 template <typename T>
 int fast_slice2d(Engine<T>& e, cx<T>* a, i64 nslices, i64 N, bool inverse, bool has_scale, T scale, int nranks, int rank,
                  void* const* peers, bool* handled);   // jtb_fast.cu
+template <typename T>
+int mixed_c2c(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, i64 n, bool inverse, bool has_scale, T scale,
+              bool* handled);   // jtb_mixed.cu
 int peer_barrier(Ctx* ctx, cudaStream_t st, void* const* flag_ptrs, int nranks, int rank, long long epoch);
 
 extern template struct Engine<double>;

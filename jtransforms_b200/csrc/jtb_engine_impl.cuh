@@ -349,6 +349,12 @@ int Engine<T>::c2c_lines(C* a, const Geo& g, i64 nlines, i64 n, bool inverse, bo
     f.has_scale = has_scale; f.scale = scale;
     return c2c_pow2(a, g, a, g, 0, nlines, ilog2(n), f);
   }
+  // smooth lengths that fit one CTA: native mixed-radix passes (the reference's FFTPACK plan)
+  {
+    bool handled = false;
+    JTB_TRY(mixed_c2c<T>(*this, a, g, nlines, n, inverse, has_scale, scale, &handled));
+    if (handled) return ST_OK;
+  }
   // Bluestein chirp-z (fft/DoubleFFT_1D.java:1920-2107); inverse = swap . forward . swap
   if (g.stride == 1 && g.c[0] == 1 && g.c[1] == 1 && g.c[2] == 1) {
     bool handled = false;

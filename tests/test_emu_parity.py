@@ -228,3 +228,20 @@ def test_fast_kernel_8192_rows(jt):
     pc.fft1d_batch(jt, "Double", 8192, 2, pad=2)
     pc.fft1d_batch(jt, "Float", 8192, 2)
     pc.fft1d_complex(jt, "Float", 4096)
+
+
+# native mixed-radix lengths (jtb_mixed.cuh): 2^a 3^b 5^c 7^d 11^e 13^f that fit one CTA
+@pytest.mark.parametrize("n", [3, 5, 6, 7, 9, 10, 11, 12, 13, 15, 100, 120, 1056, 420, 1000, 1050, 2916])
+def test_mixed_radix_1d(jt, n):
+    pc.fft1d_complex(jt, "Double", n)
+
+
+def test_mixed_radix_float_real_nd(jt):
+    pc.fft1d_complex(jt, "Float", 360)
+    pc.fft1d_real(jt, "Double", 300)
+    pc.fft1d_real(jt, "Double", 45)
+    pc.fftnd_complex(jt, "Double", (30, 42))
+    pc.fftnd_complex(jt, "Double", (12, 10, 14))
+    pc.fftnd_complex(jt, "Float", (24, 36))
+    pc.r2r(jt, "Double", "DCT", (30, 20))
+    pc.fft1d_batch(jt, "Double", 100, 7, pad=2)
