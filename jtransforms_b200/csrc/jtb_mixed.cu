@@ -63,6 +63,17 @@ int mixed_c2c(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, i64 n, bool inve
   p.n = (int)n; p.W = W; p.wfast = strided && W > 1;
   p.swap_in = inverse; p.swap_out = inverse; p.has_scale = has_scale; p.scale = scale;
   p.wtab = (const C*)d;
+  p.m_n = mix_magic((unsigned)n);
+  p.logW = 0;
+  while ((1 << p.logW) < W) ++p.logW;
+  {
+    i64 ns = 1;
+    for (int s = 0; s < p.nstages; ++s) {
+      p.m_nb[s] = mix_magic((unsigned)(n / p.radix[s]));
+      p.m_ns[s] = mix_magic((unsigned)ns);
+      ns *= p.radix[s];
+    }
+  }
   const i64 work = (i64)W * n / 4;                       // butterflies of a radix-4 stage
   const unsigned threads = work >= 512 ? 512u : (work >= 256 ? 256u : (work >= 128 ? 128u : 64u));
   const i64 nblk = (nlines + W - 1) / W;

@@ -22,10 +22,22 @@ template <typename T> struct MixedParams {
   int n, W, wfast;
   int nstages;
   int radix[MIX_MAX_STAGES];
+  // division-free indexing: x / d == __umulhi(x, magic(d)) for every x this kernel forms (x * d < 2^32)
+  unsigned m_nb[MIX_MAX_STAGES], m_ns[MIX_MAX_STAGES], m_n;
+  int logW;            // W is a power of two when wfast
   int swap_in, swap_out, has_scale;
   T scale;
   const cx<T>* wtab;   // exp(-2 pi i j / n), j < n
 };
+
+__host__ __device__ __forceinline__ unsigned mix_magic(unsigned d) { return d <= 1 ? 0u : (unsigned)(0x100000000ULL / d) + 1u; }
+__device__ __forceinline__ int mix_div(int x, unsigned magic, int d) {
+#ifdef JTB_EMU
+  (void)magic; return x / d;
+#else
+  return d <= 1 ? x : (int)__umulhi((unsigned)x, magic);
+#endif
+}
 
 template <typename C> __device__ __forceinline__ C mix_w(const C* __restrict__ w, int j) { return __ldg(w + j); }
 
@@ -78,14 +90,14 @@ __device__ __forceinline__ void dft_small(cx<T>* x, const cx<T>* __restrict__ wt
 template <typename T, int R>
 __device__ __forceinline__ void mixed_stage(const cx<T>* __restrict__ src, cx<T>* __restrict__ dst, int n, int Ns, int lines,
                                             int ld, const cx<T>* __restrict__ wtab, int tid, int nthreads, int wfast,
-                                            int W) {
+                                            int W, int logW, unsigned m_nb, unsigned m_ns) {
   typedef cx<T> C;
   const int nb = n / R;                 // butterflies per line
   const int tstep = n / (Ns * R);       // twiddle index step: W_{Ns R}^{m} = wtab[m * tstep]
   for (int idx = tid; idx < nb * lines; idx += nthreads) {
     int b, w;
-    if (wfast) { w = idx % W; b = idx / W; } else { b = idx % nb; w = idx / nb; }
-    const int k = b % Ns;
+    if (wfast) { w = idx & (W - 1); b = idx >> logW; } else { w = mix_div(idx, m_nb, nb); b = idx - w * nb; }
+    const int k = b - mix_div(b, m_ns, Ns) * Ns;
     C x[R];
 #pragma unroll
     for (int q = 0; q < R; ++q) {
@@ -119,7 +131,7 @@ template <typename T> __global__ void __launch_bounds__(512, 1) fft_mixed_kernel
   // load (coalesced along the memory-contiguous direction)
   for (int idx = tid; idx < n * W; idx += nthreads) {
     int i, w;
-    if (wfast) { w = idx % W; i = idx / W; } else { i = idx % n; w = idx / n; }
+    if (wfast) { w = idx & (W - 1); i = idx >> p.logW; } else { w = mix_div(idx, p.m_n, n); i = idx - w * n; }
     if (w < lines) {
       C z = p.in[geo_off(p.gi, line0 + w) + (i64)i * p.gi.stride];
       if (p.swap_in) z = cswap(z);
@@ -133,13 +145,13 @@ template <typename T> __global__ void __launch_bounds__(512, 1) fft_mixed_kernel
   for (int s = 0; s < p.nstages; ++s) {
     const int R = p.radix[s];
     switch (R) {
-      case 2: mixed_stage<T, 2>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W); break;
-      case 3: mixed_stage<T, 3>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W); break;
-      case 4: mixed_stage<T, 4>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W); break;
-      case 5: mixed_stage<T, 5>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W); break;
-      case 7: mixed_stage<T, 7>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W); break;
-      case 11: mixed_stage<T, 11>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W); break;
-      default: mixed_stage<T, 13>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W); break;
+      case 2: mixed_stage<T, 2>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W, p.logW, p.m_nb[s], p.m_ns[s]); break;
+      case 3: mixed_stage<T, 3>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W, p.logW, p.m_nb[s], p.m_ns[s]); break;
+      case 4: mixed_stage<T, 4>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W, p.logW, p.m_nb[s], p.m_ns[s]); break;
+      case 5: mixed_stage<T, 5>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W, p.logW, p.m_nb[s], p.m_ns[s]); break;
+      case 7: mixed_stage<T, 7>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W, p.logW, p.m_nb[s], p.m_ns[s]); break;
+      case 11: mixed_stage<T, 11>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W, p.logW, p.m_nb[s], p.m_ns[s]); break;
+      default: mixed_stage<T, 13>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W, p.logW, p.m_nb[s], p.m_ns[s]); break;
     }
     __syncthreads();
     Ns *= R;
@@ -147,7 +159,7 @@ template <typename T> __global__ void __launch_bounds__(512, 1) fft_mixed_kernel
   }
   for (int idx = tid; idx < n * W; idx += nthreads) {
     int i, w;
-    if (wfast) { w = idx % W; i = idx / W; } else { i = idx % n; w = idx / n; }
+    if (wfast) { w = idx & (W - 1); i = idx >> p.logW; } else { w = mix_div(idx, p.m_n, n); i = idx - w * n; }
     if (w < lines) {
       C z = src[wfast ? i * W + w : w * ld + i];
       if (p.has_scale) { z.x *= p.scale; z.y *= p.scale; }
