@@ -165,8 +165,8 @@ template <typename T, int LOGN, int LOGE, int W> ScatterEntry<T> make_scatter() 
 }
 template <typename T> std::vector<ScatterEntry<T>>& scatter_registry();
 template <> std::vector<ScatterEntry<double>>& scatter_registry<double>() {
-  static std::vector<ScatterEntry<double>> r = {make_scatter<double, 9, 3, 8>(), make_scatter<double, 6, 3, 8>(),
-                                                make_scatter<double, 10, 4, 8>()};
+  static std::vector<ScatterEntry<double>> r = {make_scatter<double, 9, 3, 8>(), make_scatter<double, 9, 3, 16>(),
+                                                make_scatter<double, 6, 3, 8>(), make_scatter<double, 10, 4, 8>()};
   return r;
 }
 template <> std::vector<ScatterEntry<float>>& scatter_registry<float>() {
@@ -184,8 +184,10 @@ int fast_scatter(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, int nranks
   }
   const int logn = ilog2(R);
   ScatterEntry<T>* pick = nullptr;
+  const char* ew = getenv("JTB_SCATTER_W");
+  const int wwant = ew ? atoi(ew) : 0;
   for (auto& f : scatter_registry<T>())
-    if (f.logn == logn && Cn % f.W == 0) { pick = &f; break; }
+    if (f.logn == logn && Cn % f.W == 0 && (wwant <= 0 || f.W == wwant)) { pick = &f; break; }
   if (!pick) { set_error("no fused-exchange kernel for %lld rows x %lld columns", (long long)R, (long long)Cn); return ST_UNSUPPORTED; }
   if (Ls * (Cn / pick->W) > 0x7fffffffLL || Ls * R * Cn >= (1LL << 40)) { set_error("slab too large"); return ST_UNSUPPORTED; }
   if (!(pick->attr_done & (1u << (e.ctx->device & 31)))) {
@@ -211,9 +213,12 @@ int fast_slice2d(Engine<T>& e, cx<T>* a, i64 nslices, i64 N, bool inverse, bool 
                  void* const* peers, bool* handled) {
   *handled = false;
 #ifndef JTB_EMU
-  // Opt-in (JTB_SLICE2D=1): measured on B200 at 512^3 the fused kernel moves less DRAM traffic (5.7 GB vs 8.6 GB)
-  // but is slower (1.57 ms vs 1.30 ms for the two separate passes): team-barrier stalls outweigh the L2 reuse.
-  static const bool off = getenv("JTB_SLICE2D") == nullptr;
+  // Measured on B200 at 512^3.  Single GPU: the fused kernel moves less DRAM traffic (5.7 GB vs 8.6 GB) but is
+  // slower (1.57 ms vs 1.30 ms for the two separate passes: team-barrier stalls) -> off.  With the fused exchange
+  // (peers != null) the column phase is NVLink-bound and the row phase hides under it: 8 GPUs 0.537 -> 0.497 ms
+  // -> on.  JTB_SLICE2D=0/1 overrides.
+  static const char* ev_s2d = getenv("JTB_SLICE2D");
+  const bool off = ev_s2d ? atoi(ev_s2d) == 0 : peers == nullptr;
   if (off || nslices < 1 || N != 512 || sizeof(T) != 8 || nslices > 65536) return ST_OK;
   typedef void (*kern_t)(const Slice2DParams<T>);
   kern_t kern = (kern_t)fft_slice2d_kernel<double, 9, 3, 8>;

@@ -14,7 +14,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 for mode in ("p2p", "nccl"):
-    for (S, R, Cn) in [(64, 64, 64), (16, 512, 32), (8 * world, 64, 24)]:
+    for (S, R, Cn) in [(64, 64, 64), (16, 512, 32), (8 * world, 64, 24), (2 * world, 512, 512)]:
         x = o.fill_uniform(2 * S * R * Cn, seed=11)
         want = o.complex_forward_3d(x, S, R, Cn).reshape(S, R, 2 * Cn)
         f = SlabFFT3D(S, R, Cn, device_index=local, exchange=mode)

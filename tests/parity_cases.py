@@ -180,7 +180,7 @@ def r2r(jt, prec, kind, dims):
 
 
 # ------------------------------------------------------------------ fused k2 + exchange (virtual ranks)
-def slab_scatter_virtual(lib, prec, dims, P, torch_device="cpu", dev_index=0):
+def slab_scatter_virtual(lib, prec, dims, P, torch_device="cpu", dev_index=0, fused_slices=False):
     """Runs the slab-decomposed forward transform with P *virtual* ranks inside one process: every rank's
     k3 pass and fused k2-scatter (jtb_fft3d_k2_scatter) write into P receive buffers that live on the same
     device, then each rank's k1 pass runs on its buffer.  Checks the kernel's addressing against the oracle."""
@@ -199,6 +199,12 @@ def slab_scatter_virtual(lib, prec, dims, P, torch_device="cpu", dev_index=0):
     def st():
         return C.c_void_p(torch.cuda.current_stream().cuda_stream) if torch_device != "cpu" else None
     for g in range(P):
+        if fused_slices:
+            # rows + columns + exchange through the single entry point (persistent fused kernel for 512^2 slices)
+            rc = lib.jtb_fft2d_slices_device(pcode, dev_index, C.c_void_p(locs[g].data_ptr()), Ls, R, Cn, P, g, arr, 0,
+                                             st())
+            assert rc == 0, lib.jtb_last_error()
+            continue
         assert lib.jtb_lines_c2c_device(pcode, dev_index, C.c_void_p(locs[g].data_ptr()), Cn, Ls * R, 1, 0, Cn, 1, 0,
                                         1.0, st()) == 0
         rc = lib.jtb_fft3d_k2_scatter(pcode, dev_index, C.c_void_p(locs[g].data_ptr()), Ls, R, Cn, P, g, arr, 0, st())

@@ -245,3 +245,9 @@ def test_mixed_radix_float_real_nd(jt):
     pc.fftnd_complex(jt, "Float", (24, 36))
     pc.r2r(jt, "Double", "DCT", (30, 20))
     pc.fft1d_batch(jt, "Double", 100, 7, pad=2)
+
+
+def test_slices_entry_point_virtual_ranks(jt):
+    """jtb_fft2d_slices_device with receive buffers (general path in the emulated build)"""
+    from jtransforms_b200 import _lib
+    pc.slab_scatter_virtual(_lib.get(), "Double", (4, 64, 64), 2, fused_slices=True)

@@ -18,6 +18,15 @@ def test_slab_scatter_virtual_ranks(P, dims):
     pc.slab_scatter_virtual(_lib.get(), "Double", dims, P, torch_device="cuda:0")
 
 
+@pytest.mark.parametrize("P,dims", [(8, (16, 512, 512)), (2, (8, 512, 512)), (4, (8, 64, 64))])
+def test_fused_slices_scatter_virtual_ranks(P, dims):
+    """jtb_fft2d_slices_device with receive buffers: for 512 x 512 double slices this is the persistent kernel that
+    fuses rows, columns and the exchange (the default multi-GPU path)"""
+    from jtransforms_b200 import _lib
+    _lib._lib = None
+    pc.slab_scatter_virtual(_lib.get(), "Double", dims, P, torch_device="cuda:0", fused_slices=True)
+
+
 def test_slab_two_gpus():
     import torch
     n = torch.cuda.device_count()
