@@ -504,6 +504,16 @@ template <typename T> int Engine<T>::r2r_lines(T* a, const Geo& g, i64 nlines, i
   if (scale) { f0 = (T)std::sqrt(1.0 / dn); f = (T)std::sqrt(2.0 / dn); }
   else if (p2) { f0 = f = (T)1; }
   else { f0 = (T)(0.5 / dn); f = (T)(1.0 / dn); }
+  if (p2) {   // fused inverse kernels (jtb_r2r_inv.cuh)
+    bool handled = false;
+    if (g.stride == 1 && g.c[0] == 1 && g.c[1] == 1 && g.c[2] == 1) {
+      JTB_TRY(fast_r2r_rows_inv<T>(*this, a, g.d[3], nlines, n, kind, f0, f, &handled));
+    } else if (g.stride > 1 && g.d[0] == 1 && g.c[1] == 1 && g.c[2] == 1 && g.c[0] == g.stride &&
+               nlines % g.c[0] == 0 && (nlines == g.c[0] || g.d[3] >= n * g.stride)) {
+      JTB_TRY(fast_r2r_cols_inv<T>(*this, a, n, g.c[0], nlines / g.c[0], g.d[3], kind, f0, f, &handled));
+    }
+    if (handled) return ST_OK;
+  }
   return staged_lines<T>(*this, a, g, nlines, n, PRE_DCT3, POST_DCT3, dst, true, f0, f, (T)1, (T)1, dtw);
 }
 

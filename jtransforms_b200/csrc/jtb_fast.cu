@@ -20,7 +20,7 @@ template <typename T, int LOGN, int LOGE, bool STRIDED, int W> FastEntry<T> make
   FastEntry<T> e;
   e.logn = LOGN; e.loge = LOGE; e.strided = STRIDED; e.W = W; e.threads = W * S::TPL;
   e.twcount = FastTw<S>::COUNT;
-  e.smem = (int)((FastAddr<T, S, STRIDED, W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
+  e.smem = (int)((FastAddr<T, S, STRIDED, W>::TILE + FastTw<S>::COUNT_SM) * sizeof(cx<T>));
   e.nstages = S::S;
   for (int s = 0; s < JTB_MAX_STAGES; ++s) e.bits[s] = s < S::S ? S::bits(s) : 0;
   e.kern = fft_fast_kernel<T, LOGN, LOGE, STRIDED, W>;
@@ -140,6 +140,34 @@ int fast_c2c(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, int logn, bool in
   }
   const i64 nblk = ((nlines + pick->W - 1) / pick->W + p.reps - 1) / p.reps;
   if (nblk > 0x7fffffffLL) return ST_OK;
+  p.ldhint = 0; p.raster = 1;
+  int cluster = 1;
+#ifndef JTB_EMU
+  if (strided) {
+    // tuning knobs (strided passes): CTAs of a cluster start together, so the 128-byte pieces that
+    // adjacent column groups read from one row reach DRAM close in time; L2::256B asks L2 for the pair in one burst
+    static const char* ec = getenv("JTB_CLUSTER");
+    static const char* eh = getenv("JTB_LDHINT");
+    cluster = ec ? atoi(ec) : 1;
+    p.ldhint = eh ? atoi(eh) : 0;
+    static const char* er2 = getenv("JTB_RASTER");
+    p.raster = er2 ? atoi(er2) : 1;
+    if (p.raster < 1 || nblk % p.raster) p.raster = 1;
+    if (cluster < 1 || cluster > 8 || (cluster & (cluster - 1))) cluster = 1;
+    while (cluster > 1 && nblk % cluster) cluster >>= 1;
+  }
+  if (cluster > 1) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)nblk); cfg.blockDim = dim3((unsigned)pick->threads);
+    cfg.dynamicSmemBytes = (size_t)pick->smem; cfg.stream = e.st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    JTB_CUDA(cudaLaunchKernelEx(&cfg, pick->kern, p));
+  } else
+#endif
   JTB_LAUNCH(pick->kern, (unsigned)nblk, (unsigned)pick->threads, (size_t)pick->smem, e.st, p);
   JTB_CUDA(cudaGetLastError());
   e.ctx->launches++;
@@ -158,7 +186,7 @@ template <typename T, int LOGN, int LOGE, int W> ScatterEntry<T> make_scatter() 
   typedef Sched<LOGN, LOGE> S;
   ScatterEntry<T> e;
   e.logn = LOGN; e.loge = LOGE; e.W = W; e.threads = W * S::TPL;
-  e.smem = (int)((FastAddr<T, S, true, W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
+  e.smem = (int)((FastAddr<T, S, true, W>::TILE + FastTw<S>::COUNT_SM) * sizeof(cx<T>));
   e.kern = fft_scatter_kernel<T, LOGN, LOGE, W>;
   e.attr_done = 0;
   return e;
@@ -226,7 +254,7 @@ int fast_slice2d(Engine<T>& e, cx<T>* a, i64 nslices, i64 N, bool inverse, bool 
   const int threads = 8 * S::TPL;
   const size_t tile = FastAddr<double, S, false, 8>::TILE > FastAddr<double, S, true, 8>::TILE
                           ? FastAddr<double, S, false, 8>::TILE : FastAddr<double, S, true, 8>::TILE;
-  const size_t smem = (tile + FastTw<S>::COUNT) * sizeof(double2);
+  const size_t smem = (tile + FastTw<S>::COUNT_SM) * sizeof(double2);
   static bool attr_done[16] = {false};
   static int occ[16] = {0}, sms[16] = {0};
   const int dv = e.ctx->device & 15;

@@ -11,6 +11,10 @@
 #pragma once
 #include "jtb_tile.cuh"
 
+#ifndef JTB_TW_DERIVE
+#define JTB_TW_DERIVE 0
+#endif
+
 namespace jtb {
 
 template <typename T> struct FastParams {
@@ -25,7 +29,72 @@ template <typename T> struct FastParams {
   T scale;
   const cx<T>* twg;  // base twiddles, layout below (fast_twiddle_count entries)
   int reps;          // strided layout: consecutive groups of W lines handled by one CTA (TLB / launch amortisation)
+  int ldhint;        // strided layout: 1 = loads carry the L2::256B prefetch hint (the neighbouring CTA's 128 B)
+  int raster;        // strided layout: > 1 = CTA b works on column group (b % raster) * (grid / raster) + b / raster
 };
+
+// 16-byte / 8-byte global load with the L2 256-byte prefetch-size hint: a strided pass reads 128-byte pieces whose
+// neighbours are read by the adjacent CTA a little later; the hint lets L2 fetch both halves with one DRAM burst.
+template <typename C> __device__ __forceinline__ C ld_l2_256(const C* p) {
+#ifdef JTB_EMU
+  return *p;
+#else
+  C r;
+  if (sizeof(C) == 16) {
+    double x, y;
+    asm volatile("ld.global.L2::256B.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "l"(p));
+    r.x = x; r.y = y;
+  } else {
+    float x, y;
+    asm volatile("ld.global.L2::256B.v2.f32 {%0,%1}, [%2];" : "=f"(x), "=f"(y) : "l"(p));
+    r.x = x; r.y = y;
+  }
+  return r;
+#endif
+}
+
+// four consecutive reals with one request: 256-bit LDG/STG for double (sm_100a: ld.global.v4.f64, 32-byte aligned),
+// 128-bit for float.  A 32-byte-strided pair of 16-byte accesses would touch every sector twice.
+__device__ __forceinline__ void ld4(const double* p, double& a, double& b, double& c, double& d) {
+#ifdef JTB_EMU
+  a = p[0]; b = p[1]; c = p[2]; d = p[3];
+#else
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+#endif
+}
+__device__ __forceinline__ void ld4(const float* p, float& a, float& b, float& c, float& d) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  a = v.x; b = v.y; c = v.z; d = v.w;
+}
+__device__ __forceinline__ void st4(double* p, double a, double b, double c, double d) {
+#ifdef JTB_EMU
+  p[0] = a; p[1] = b; p[2] = c; p[3] = d;
+#else
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#endif
+}
+__device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) {
+  float4 v; v.x = a; v.y = b; v.z = c; v.w = d;
+  *reinterpret_cast<float4*>(p) = v;
+}
+
+// The DCT/DST twiddles a pair (k, N-k) of a length-n = 2N line needs, all from ONE table read D = exp(-i pi k/2n):
+//   D(N-k) = c conj(D), D(N+k) = c D, D(n-k) = -i conj(D), c = exp(-i pi/4);  exp(-2 pi i k/n) = D^4.
+template <typename C> __device__ __forceinline__ C dct_tw_nmk(C d) {   // D(N-k)
+  typedef decltype(d.x) T;
+  const T s = (T)0.70710678118654752440084436210485L;
+  C r; r.x = s * (d.x - d.y); r.y = -s * (d.x + d.y); return r;
+}
+template <typename C> __device__ __forceinline__ C dct_tw_npk(C d) {   // D(N+k)
+  typedef decltype(d.x) T;
+  const T s = (T)0.70710678118654752440084436210485L;
+  C r; r.x = s * (d.x + d.y); r.y = s * (d.y - d.x); return r;
+}
+template <typename C> __device__ __forceinline__ C dct_tw_pow4(C d) {  // D^4 = exp(-2 pi i k/n)
+  C d2; d2.x = (d.x - d.y) * (d.x + d.y); d2.y = 2 * d.x * d.y;
+  C d4; d4.x = (d2.x - d2.y) * (d2.x + d2.y); d4.y = 2 * d2.x * d2.y;
+  return d4;
+}
 
 // base twiddle table: for stage s >= 1 and j < bits(s):  tab[toff(s) + j*ns(s) + k] = exp(-2 pi i 2^j k / (ns(s) 2^bits(s)))
 // Only the tables of the early stages (few entries, every entry reused by many threads of the CTA) are staged in
@@ -73,9 +142,17 @@ template <typename T, typename S, int s, bool STRIDED, int W> struct FastStage {
         const int k = (t + m * S::TPL) & (NS - 1);
         constexpr int TOFF = FastTw<S>::toff(s);
         cx<T> tw[R];
+#if JTB_TW_DERIVE
+        // one table read per butterfly; w^2k, w^4k, w^8k by squaring (trades 2-3 complex multiplies for the
+        // shared-memory / L1 wavefronts of the other base twiddles)
+        tw[1] = FastTw<S>::in_smem(s) ? twt[TOFF + k] : __ldg(twg + TOFF + k);
+#pragma unroll
+        for (int j = 1; j < LOGR; ++j) tw[1 << j] = cmul(tw[1 << (j - 1)], tw[1 << (j - 1)]);
+#else
 #pragma unroll
         for (int j = 0; j < LOGR; ++j)
           tw[1 << j] = FastTw<S>::in_smem(s) ? twt[TOFF + j * NS + k] : __ldg(twg + TOFF + j * NS + k);
+#endif
 #pragma unroll
         for (int r = 3; r < R; ++r) {
           // highest set bit h of r; r = 2^h + rest
@@ -137,7 +214,9 @@ fft_fast_kernel(const FastParams<T> p) {
   for (int i = tid; i < FastTw<S>::COUNT_SM; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
 
   for (int rep = 0; rep < (STRIDED ? p.reps : 1); ++rep) {
-    const i64 line0 = ((i64)blockIdx.x * (STRIDED ? p.reps : 1) + rep) * W;
+    i64 blk = blockIdx.x;
+    if (STRIDED && p.raster > 1) blk = (i64)(blockIdx.x % p.raster) * (gridDim.x / p.raster) + blockIdx.x / p.raster;
+    const i64 line0 = (blk * (STRIDED ? p.reps : 1) + rep) * W;
     if (line0 >= p.nlines) break;
     C* base;
     int es;
@@ -153,7 +232,10 @@ fft_fast_kernel(const FastParams<T> p) {
       es = 1;
     }
     C v[S::E];
-    if (valid) {
+    if (STRIDED && p.ldhint) {
+#pragma unroll
+      for (int q = 0; q < S::E; ++q) v[q] = ld_l2_256(base + (t + q * S::TPL) * es);
+    } else if (valid) {
 #pragma unroll
       for (int q = 0; q < S::E; ++q) v[q] = base[(t + q * S::TPL) * es];
     } else {

@@ -21,7 +21,7 @@ template <typename T, int LOGN, int LOGE, bool SIN, int MODE, int W> F2Entry<T> 
   typedef Sched<LOGN, LOGE> S;
   F2Entry<T> e;
   e.logn = LOGN; e.loge = LOGE; e.sin = SIN; e.mode = MODE; e.W = W; e.threads = W * S::TPL;
-  e.smem = (int)((FastAddr<T, S, SIN, W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
+  e.smem = (int)((FastAddr<T, S, SIN, W>::TILE + FastTw<S>::COUNT_SM) * sizeof(cx<T>));
   e.kern = fft_fast2_kernel<T, LOGN, LOGE, SIN, MODE, W>;
   e.attr_done = 0;
   e.min_lines = min_lines;
@@ -39,16 +39,18 @@ template <> std::vector<F2Entry<double>>& reg2<double>() {
       mk2<double, 10, 4, false, FM_TRANSPOSE, 8>(),
       mk2<double, 11, 4, false, FM_TRANSPOSE, 4>(),
       // second pass, strided lines (row permutation only)
-      mk2<double, 6, 3, true, FM_PLAIN, 32>(), mk2<double, 7, 4, true, FM_PLAIN, 16>(),
+      mk2<double, 6, 3, true, FM_PLAIN, 32>(), mk2<double, 7, 4, true, FM_PLAIN, 16>(), mk2<double, 5, 3, true, FM_PLAIN, 32>(),
       // real-forward rows
       mk2<double, 8, 4, false, FM_RFFT, 8>(), mk2<double, 9, 3, false, FM_RFFT, 4>(), mk2<double, 10, 3, false, FM_RFFT, 2>(),
-      mk2<double, 11, 3, false, FM_RFFT, 1>(), mk2<double, 12, 3, false, FM_RFFT, 1>(),
+      mk2<double, 11, 3, false, FM_RFFT, 1>(), mk2<double, 12, 3, false, FM_RFFT, 1>(), mk2<double, 11, 4, false, FM_RFFT, 2>(),
   };
   return r;
 }
 template <> std::vector<F2Entry<float>>& reg2<float>() {
   static std::vector<F2Entry<float>> r = {
+      mk2<float, 6, 3, true, FM_TWID, 32>(), mk2<float, 7, 4, true, FM_TWID, 16>(),
       mk2<float, 9, 3, true, FM_TWID, 16>(), mk2<float, 10, 4, true, FM_TWID, 16>(),
+      mk2<float, 5, 3, true, FM_PLAIN, 32>(), mk2<float, 6, 3, true, FM_PLAIN, 32>(), mk2<float, 7, 4, true, FM_PLAIN, 16>(),
       mk2<float, 9, 3, false, FM_TRANSPOSE, 16>(), mk2<float, 10, 4, false, FM_TRANSPOSE, 16>(),
       mk2<float, 11, 4, false, FM_TRANSPOSE, 8>(),
       mk2<float, 10, 4, false, FM_RFFT, 4>(), mk2<float, 11, 4, false, FM_RFFT, 2>(),
@@ -152,7 +154,7 @@ int fast_fourstep_strided(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, int 
   if (g_fast2_off || nlines <= 0) return ST_OK;
   if (!(g.stride > 1 && g.d[0] == 1 && g.c[1] == 1 && g.c[2] == 1 && g.c[0] > 1 && nlines % g.c[0] == 0)) return ST_OK;
   F2Entry<T>*f1 = nullptr, *f2 = nullptr;
-  for (int la = (logn + 1) / 2; la <= logn - 6 + 0 && !f1; ++la) {
+  for (int la = (logn + 1) / 2; la <= logn - 5 && !f1; ++la) {
     F2Entry<T>* x = find2<T>(la, true, FM_TWID);
     F2Entry<T>* y = find2<T>(logn - la, true, FM_PLAIN);
     if (x && y) { f1 = x; f2 = y; }
@@ -207,6 +209,8 @@ int fast_rfft_fwd(Engine<T>& e, cx<T>* a, i64 dist, i64 nlines, int logN, bool* 
   *handled = false;
   if (g_fast2_off || nlines <= 0) return ST_OK;
   F2Entry<T>* f = find2<T>(logN, false, FM_RFFT);
+  static const char* ele = getenv("JTB_ROW_LOGE");
+  if (ele) for (auto& x : reg2<T>()) if (x.logn == logN && !x.sin && x.mode == FM_RFFT && x.loge == atoi(ele)) { f = &x; break; }
   if (!f) return ST_OK;
   const cx<T>* tw[JTB_MAX_STAGES];
   const cx<T>* rtw;
@@ -231,7 +235,7 @@ template <typename T, int LOGN, int LOGE, int KIND, int W> RowEntry<T> mkrow() {
   typedef Sched<LOGN, LOGE> S;
   RowEntry<T> e;
   e.logn = LOGN; e.loge = LOGE; e.kind = KIND; e.W = W; e.threads = W * S::TPL;
-  e.smem = (int)((FastAddr<T, S, false, W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
+  e.smem = (int)((FastAddr<T, S, false, W>::TILE + FastTw<S>::COUNT_SM) * sizeof(cx<T>));
   e.kern = fft_r2r_row_kernel<T, LOGN, LOGE, KIND, W>;
   e.attr_done = 0;
   return e;
@@ -239,12 +243,15 @@ template <typename T, int LOGN, int LOGE, int KIND, int W> RowEntry<T> mkrow() {
 #define JTB_ROWS(T, LOGN, LOGE, W) mkrow<T, LOGN, LOGE, RK_DCT, W>(), mkrow<T, LOGN, LOGE, RK_DST, W>(), mkrow<T, LOGN, LOGE, RK_DHT, W>()
 template <typename T> std::vector<RowEntry<T>>& rowreg();
 template <> std::vector<RowEntry<double>>& rowreg<double>() {
-  static std::vector<RowEntry<double>> r = {JTB_ROWS(double, 12, 3, 1), JTB_ROWS(double, 11, 3, 1), JTB_ROWS(double, 10, 3, 2),
-                                            JTB_ROWS(double, 9, 3, 4), JTB_ROWS(double, 8, 4, 8)};
+  static std::vector<RowEntry<double>> r = {JTB_ROWS(double, 12, 4, 1), JTB_ROWS(double, 12, 3, 1), JTB_ROWS(double, 11, 3, 1), JTB_ROWS(double, 11, 4, 2), JTB_ROWS(double, 10, 3, 2),
+                                            JTB_ROWS(double, 9, 3, 4), JTB_ROWS(double, 8, 4, 8), JTB_ROWS(double, 7, 4, 16),
+                                            JTB_ROWS(double, 6, 3, 16), JTB_ROWS(double, 5, 3, 32)};
   return r;
 }
 template <> std::vector<RowEntry<float>>& rowreg<float>() {
-  static std::vector<RowEntry<float>> r = {JTB_ROWS(float, 12, 4, 1), JTB_ROWS(float, 11, 4, 2), JTB_ROWS(float, 10, 4, 4)};
+  static std::vector<RowEntry<float>> r = {JTB_ROWS(float, 12, 4, 1), JTB_ROWS(float, 11, 4, 2), JTB_ROWS(float, 10, 4, 4),
+                                           JTB_ROWS(float, 9, 3, 8),  JTB_ROWS(float, 8, 4, 16), JTB_ROWS(float, 7, 4, 16),
+                                           JTB_ROWS(float, 6, 3, 32), JTB_ROWS(float, 5, 3, 32)};
   return r;
 }
 
@@ -256,7 +263,7 @@ template <typename T, int LOGN, int LOGE, int W, int PRE> PreEntry<T> mkpre() {
   x.logn = LOGN; x.pre = PRE;
   F2Entry<T>& e = x.e;
   e.logn = LOGN; e.loge = LOGE; e.sin = 1; e.mode = FM_TWID; e.W = W; e.threads = W * S::TPL;
-  e.smem = (int)((FastAddr<T, S, true, W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
+  e.smem = (int)((FastAddr<T, S, true, W>::TILE + FastTw<S>::COUNT_SM) * sizeof(cx<T>));
   e.kern = fft_fast2_kernel<T, LOGN, LOGE, true, FM_TWID, W, PRE>;
   e.attr_done = 0; e.min_lines = 0;
   for (int d = 0; d < 16; ++d) e.twg[d] = nullptr;
@@ -269,7 +276,8 @@ template <> std::vector<PreEntry<double>>& prereg<double>() {
   return r;
 }
 template <> std::vector<PreEntry<float>>& prereg<float>() {
-  static std::vector<PreEntry<float>> r;
+  static std::vector<PreEntry<float>> r = {mkpre<float, 6, 3, 32, PRE_PERM_DCT>(), mkpre<float, 6, 3, 32, PRE_PERM_DST>(),
+                                           mkpre<float, 7, 4, 16, PRE_PERM_DCT>(), mkpre<float, 7, 4, 16, PRE_PERM_DST>()};
   return r;
 }
 }  // namespace
@@ -284,18 +292,18 @@ template <typename T, int LOGN, int LOGE, int W> PairEntry<T> mkpair() {
   typedef Sched<LOGN, LOGE> S;
   PairEntry<T> e;
   e.logn = LOGN; e.loge = LOGE; e.W = W; e.threads = 2 * W * S::TPL;
-  e.smem = (int)((FastAddr<T, S, true, 2 * W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
+  e.smem = (int)((FastAddr<T, S, true, 2 * W>::TILE + FastTw<S>::COUNT_SM) * sizeof(cx<T>));
   e.kern = fft_colpair_kernel<T, LOGN, LOGE, W>;
   e.attr_done = 0;
   return e;
 }
 template <typename T> std::vector<PairEntry<T>>& pairreg();
 template <> std::vector<PairEntry<double>>& pairreg<double>() {
-  static std::vector<PairEntry<double>> r = {mkpair<double, 6, 3, 32>(), mkpair<double, 7, 4, 16>()};
+  static std::vector<PairEntry<double>> r = {mkpair<double, 6, 3, 32>(), mkpair<double, 7, 4, 16>(), mkpair<double, 5, 3, 32>()};
   return r;
 }
 template <> std::vector<PairEntry<float>>& pairreg<float>() {
-  static std::vector<PairEntry<float>> r;
+  static std::vector<PairEntry<float>> r = {mkpair<float, 6, 3, 32>(), mkpair<float, 7, 4, 16>(), mkpair<float, 5, 3, 32>()};
   return r;
 }
 
@@ -306,9 +314,13 @@ template <typename T>
 int fast_r2r_rows(Engine<T>& e, T* a, i64 dist, i64 nlines, i64 n, int kind, T f0, T f, bool* handled) {
   *handled = false;
   if (g_fast2_off || nlines <= 0 || !is_pow2(n) || n < 4 || (dist % 2) || ((uintptr_t)a % sizeof(cx<T>))) return ST_OK;
+  if (kind != RK_DHT && ((dist % 4) || ((uintptr_t)a % (4 * sizeof(T))))) return ST_OK;   // 4-real vector loads
   const int logN = ilog2(n) - 1;
   RowEntry<T>* r = nullptr;
-  for (auto& x : rowreg<T>()) if (x.logn == logN && x.kind == kind) { r = &x; break; }
+  static const char* ele = getenv("JTB_ROW_LOGE");   // tuning knob: prefer the variant with this radix
+  const int want_loge = ele ? atoi(ele) : 0;
+  for (auto& x : rowreg<T>()) if (x.logn == logN && x.kind == kind && (!want_loge || x.loge == want_loge)) { r = &x; break; }
+  if (!r) for (auto& x : rowreg<T>()) if (x.logn == logN && x.kind == kind) { r = &x; break; }
   if (!r) return ST_OK;
   if (!(r->attr_done & (1u << (e.ctx->device & 31)))) {
     JTB_CUDA(cudaFuncSetAttribute(r->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, r->smem));
@@ -338,9 +350,11 @@ int fast_r2r_cols(Engine<T>& e, T* a, i64 n, i64 Cn, i64 batches, i64 bdist, int
   typedef cx<T> C;
   *handled = false;
   if (g_fast2_off || !is_pow2(n) || (Cn % 2) || (bdist % 2) || ((uintptr_t)a % sizeof(C)) || batches < 1) return ST_OK;
+  JTB_TRY(fast_r2r_cols_single<T>(e, a, n, Cn, batches, bdist, kind, false, f0, f, handled));   // n <= 1024: one pass
+  if (*handled) return ST_OK;
   const int logn = ilog2(n);
   F2Entry<T>*f1 = nullptr, *f2 = nullptr;
-  for (int la = (logn + 1) / 2; la <= logn - 6 && !f1; ++la) {
+  for (int la = (logn + 1) / 2; la <= logn - 5 && !f1; ++la) {
     F2Entry<T>* x = nullptr;
     if (kind == RK_DHT) x = find2<T>(la, true, FM_TWID);
     else for (auto& pe : prereg<T>()) if (pe.logn == la && pe.pre == (kind == RK_DCT ? PRE_PERM_DCT : PRE_PERM_DST)) x = &pe.e;
@@ -424,7 +438,7 @@ template <typename T, int LOGN, int LOGE, int W, int MODE, int PRE> F2Entry<T> m
   typedef Sched<LOGN, LOGE> S;
   F2Entry<T> e;
   e.logn = LOGN; e.loge = LOGE; e.sin = 1; e.mode = MODE; e.W = W; e.threads = W * S::TPL;
-  e.smem = (int)((FastAddr<T, S, true, W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
+  e.smem = (int)((FastAddr<T, S, true, W>::TILE + FastTw<S>::COUNT_SM) * sizeof(cx<T>));
   e.kern = fft_fast2_kernel<T, LOGN, LOGE, true, MODE, W, PRE>;
   e.attr_done = 0; e.min_lines = 0;
   for (int d = 0; d < 16; ++d) e.twg[d] = nullptr;
@@ -439,7 +453,7 @@ template <typename T, int LOGN, int LOGE, int W> ConvEntry<T> mkconv() {
   typedef Sched<LOGN, LOGE> S;
   ConvEntry<T> e;
   e.logn = LOGN; e.loge = LOGE; e.W = W; e.threads = W * S::TPL;
-  e.smem = (int)((FastAddr<T, S, false, W>::TILE + FastTw<S>::COUNT) * sizeof(cx<T>));
+  e.smem = (int)((FastAddr<T, S, false, W>::TILE + FastTw<S>::COUNT_SM) * sizeof(cx<T>));
   e.kern = fft_conv_kernel<T, LOGN, LOGE, W>;
   e.attr_done = 0;
   return e;

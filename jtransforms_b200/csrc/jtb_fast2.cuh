@@ -43,7 +43,9 @@ template <typename T> struct Fast2Params {
   int swap_out1;      // FM_CHIRP_OUT: undo the swapped-domain inverse before the chirp multiply
 };
 
-enum { PRE_NONE = 0, PRE_PERM_DCT = 1, PRE_PERM_DST = 2, PRE_CHIRP = 3 };
+// PRE_UNPERM_* (second pass of a long strided inverse DCT/DST column, jtb_r2r_inv.cuh) act on the STORE: output
+// element m = j*gmod + (g % gmod) goes to row 2m (m < n/2) or 2(n-1-m)+1 of the array, DST negates the odd rows.
+enum { PRE_NONE = 0, PRE_PERM_DCT = 1, PRE_PERM_DST = 2, PRE_CHIRP = 3, PRE_UNPERM_DCT = 4, PRE_UNPERM_DST = 5 };
 
 template <typename T> __device__ __forceinline__ cx<T> fs_tw2(const Fast2Params<T>& p, int m) {
   return cmul(__ldg(p.fsA + (m >> p.fs_logL)), __ldg(p.fsB + (m & ((1 << p.fs_logL) - 1))));
@@ -85,12 +87,14 @@ fft_fast2_kernel(const Fast2Params<T> p) {
       }
       v[q] = z;
     }
-  } else if (valid && PRE != PRE_NONE) {
+  } else if (valid && (PRE == PRE_PERM_DCT || PRE == PRE_PERM_DST)) {
     const C* src = p.in + g_hi * p.in_gdist2 + c * p.in_cdist;
 #pragma unroll
     for (int q = 0; q < S::E; ++q) {
+      // pre_n = gmod * N (host): j >= pre_n/2  <=>  t + q*TPL >= N/2  <=>  q >= E/2, a compile-time property of q, so
+      // the DST sign folds into the first butterfly and all loads issue back to back
       const i64 j = (i64)(t + q * S::TPL) * p.gmod + g_lo;
-      const bool second = 2 * j >= p.pre_n;
+      const bool second = q >= S::E / 2;
       const i64 row = second ? 2 * (p.pre_n - 1 - j) + 1 : 2 * j;
       C z = src[row * p.pre_s];
       if (PRE == PRE_PERM_DST && second) { z.x = -z.x; z.y = -z.y; }
@@ -147,7 +151,18 @@ fft_fast2_kernel(const Fast2Params<T> p) {
 #pragma unroll
       for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
     }
-    if (valid) {
+    if (valid && (PRE == PRE_UNPERM_DCT || PRE == PRE_UNPERM_DST)) {
+      C* dst = p.out + g_hi * p.out_gdist2 + c * p.out_cdist;
+#pragma unroll
+      for (int q = 0; q < S::E; ++q) {
+        const i64 m = (i64)(t + q * S::TPL) * p.gmod + g_lo;
+        const bool second = q >= S::E / 2;          // pre_n = gmod * N
+        const i64 row = second ? 2 * (p.pre_n - 1 - m) + 1 : 2 * m;
+        C z = v[q];
+        if (PRE == PRE_UNPERM_DST && second) { z.x = -z.x; z.y = -z.y; }
+        dst[row * p.pre_s] = z;
+      }
+    } else if (valid) {
       C* dst = p.out + g_lo * p.out_gdist + g_hi * p.out_gdist2 + c * p.out_cdist;
 #pragma unroll
       for (int q = 0; q < S::E; ++q) dst[(t + q * S::TPL) * p.out_stride] = v[q];
@@ -174,9 +189,11 @@ fft_fast2_kernel(const Fast2Params<T> p) {
   } else if (MODE == FM_RFFT) {
     // Z = FFT_N(x[2j] + i x[2j+1]);  X[k] = (Z[k] + conj Z[N-k])/2 - i/2 w^k (Z[k] - conj Z[N-k]),  w = exp(-2 pi i/(2N))
     // packed: out[0] = (Re X[0], Re X[N]);  out[k] = X[k], 0 < k < N
+    // Z[k] for k < N/2 stays in registers; only the upper half is handed over (unpadded: unit-stride accesses)
     if (S::S > 1) __syncthreads();
+    C* half = sm + w * S::N;
 #pragma unroll
-    for (int q = 0; q < S::E; ++q) sm[A::at(t + q * S::TPL, w)] = v[q];
+    for (int q = S::E / 2; q < S::E; ++q) half[t + q * S::TPL] = v[q];
     __syncthreads();
     if (valid) {
       C* dst = p.out + g_lo * p.out_gdist + g_hi * p.out_gdist2 + c * p.out_cdist;
@@ -185,13 +202,13 @@ fft_fast2_kernel(const Fast2Params<T> p) {
       for (int q = 0; q < S::E / 2; ++q) {
         const int k = t + q * S::TPL;   // 0 .. N/2 - 1
         if (k == 0) {
-          const C z = sm[A::at(0, w)];
+          const C z = v[0];
           dst[0] = mk<T>(z.x + z.y, z.x - z.y);
-          const C zm = sm[A::at(S::N / 2, w)];
+          const C zm = v[S::E / 2];
           dst[S::N / 2] = mk<T>(zm.x, -zm.y);
         } else {
-          const C a = sm[A::at(k, w)];
-          const C b = sm[A::at(S::N - k, w)];
+          const C a = v[q];
+          const C b = half[S::N - k];
           const C wk = __ldg(p.rtw + k);
           const C ev = mk<T>((a.x + b.x) * hf, (a.y - b.y) * hf);
           const C df = mk<T>((a.x - b.x) * hf, (a.y + b.y) * hf);
@@ -293,68 +310,61 @@ fft_r2r_row_kernel(const RowR2RParams<T> p) {
   typedef Sched<LOGN, LOGE> S;
   typedef cx<T> C;
   typedef FastAddr<T, S, false, W> A;
-  constexpr int N = S::N, n = 2 * S::N;
+  constexpr int N = S::N, n = 2 * S::N, H = S::E / 2;
   JTB_DYN_SMEM(smem_raw);
   C* sm = reinterpret_cast<C*>(smem_raw);
-  T* smr = reinterpret_cast<T*>(smem_raw);          // the real line(s), aliasing the exchange tile
   C* twt = sm + A::TILE;
   const int tid = threadIdx.x;
   const int t = tid % S::TPL, w = tid / S::TPL;
   for (int i = tid; i < FastTw<S>::COUNT_SM; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
   const i64 line0 = (i64)blockIdx.x * W;
-  const int nl = (p.nlines - line0 < W) ? (int)(p.nlines - line0) : W;
-  const bool valid = w < nl;
-  // coalesced load of the lines, stored in shared memory already permuted (Makhoul: v[u] = x[2u],
-  // v[n-1-u] = x[2u+1]; DST additionally negates the odd samples) so that the gather below is one conflict-free
-  // 16-byte read per element: z[j] = (v[2j], v[2j+1])
-  {
-    // W*N complex loads by W*TPL threads = exactly E per thread: all issued before the first is consumed
-    const C* src = reinterpret_cast<const C*>(p.a);
-    C xr[S::E];
-#pragma unroll
-    for (int it = 0; it < S::E; ++it) {
-      const int idx = tid + it * (W * S::TPL);
-      const int ww = idx / N, u = idx - ww * N;
-      xr[it] = (ww < nl) ? src[((line0 + ww) * p.dist) / 2 + u] : mk<T>(0, 0);
-    }
-#pragma unroll
-    for (int it = 0; it < S::E; ++it) {
-      const int idx = tid + it * (W * S::TPL);
-      const int ww = idx / N, u = idx - ww * N;
-      if (KIND == RK_DHT) reinterpret_cast<C*>(smr)[ww * N + u] = xr[it];
-      else {
-        T* vs = smr + ww * n;
-        vs[u] = xr[it].x;
-        vs[n - 1 - u] = (KIND == RK_DST) ? -xr[it].y : xr[it].y;
-      }
-    }
-  }
-  __syncthreads();
+  const bool valid = line0 + w < p.nlines;
+  T* xl = p.a + (valid ? (line0 + w) * p.dist : 0);
+  C* half = sm + w * N;          // unpadded line buffer for the half-line hand-overs (conflict-free: unit stride)
   C v[S::E];
-  if (valid) {
-    const C* z = reinterpret_cast<const C*>(smr + w * n);
+  // z[j] = v[2j] + i v[2j+1] of the Makhoul-permuted line v[u] = x[2u], v[n-1-u] = x[2u+1] (DST: odd samples negated):
+  //   z[m] = (x[4m], x[4m+2]) and z[N-1-m] = (x[4m+3], x[4m+1]) for m < N/2.
+  // A thread reads the 32 contiguous bytes x[4m..4m+3] of ITS m = t + q*TPL (q < E/2), keeps z[m] in registers and
+  // hands z[N-1-m] to its owner (thread TPL-1-t) through shared memory: one half-line exchange instead of staging
+  // the whole line and gathering it back.  DHT has no permutation: z[j] is one 16-byte load.
+  if (KIND == RK_DHT) {
 #pragma unroll
-    for (int q = 0; q < S::E; ++q) v[q] = z[t + q * S::TPL];
+    for (int q = 0; q < S::E; ++q) v[q] = valid ? reinterpret_cast<const C*>(xl)[t + q * S::TPL] : mk<T>(0, 0);
   } else {
+    T x0[H], x1[H], x2[H], x3[H];
 #pragma unroll
-    for (int q = 0; q < S::E; ++q) v[q] = mk<T>(0, 0);
+    for (int q = 0; q < H; ++q) {
+      const int m = t + q * S::TPL;
+      if (valid) ld4(xl + 4 * m, x0[q], x1[q], x2[q], x3[q]);
+      else x0[q] = x1[q] = x2[q] = x3[q] = 0;
+    }
+#pragma unroll
+    for (int q = 0; q < H; ++q) {
+      const int m = t + q * S::TPL;
+      v[q] = mk<T>(x0[q], x2[q]);
+      half[N - 1 - m] = (KIND == RK_DST) ? mk<T>(-x3[q], -x1[q]) : mk<T>(x3[q], x1[q]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = H; q < S::E; ++q) v[q] = half[t + q * S::TPL];
+    __syncthreads();
   }
-  __syncthreads();
   FastLoop<T, S, 0, false, W>::run(v, sm, twt, t, w, p.twg);
+  // real split: V[k] needs Z[k] (own registers, k < N/2) and Z[N-k] (upper half, handed over through shared memory)
   if (S::S > 1) __syncthreads();
 #pragma unroll
-  for (int q = 0; q < S::E; ++q) sm[A::at(t + q * S::TPL, w)] = v[q];
+  for (int q = H; q < S::E; ++q) half[t + q * S::TPL] = v[q];
   __syncthreads();
   if (!valid) return;
-  T* out = p.a + (line0 + w) * p.dist;
+  T* out = xl;
   const T hf = (T)0.5;
 #pragma unroll
-  for (int q = 0; q < S::E / 2; ++q) {
+  for (int q = 0; q < H; ++q) {
     const int k = t + q * S::TPL;     // 0 .. N/2 - 1 ; pair (k, N - k)
     if (k == 0) {
-      const C z0 = sm[A::at(0, w)];
+      const C z0 = v[0];
       const T V0 = z0.x + z0.y, VN = z0.x - z0.y;          // V[0], V[N] (both real)
-      const C zm = sm[A::at(N / 2, w)];
+      const C zm = v[H];                                     // Z[N/2] (thread 0 owns index (E/2)*TPL)
       const C Vh = mk<T>(zm.x, -zm.y);                      // V[N/2] = conj Z[N/2]
       if (KIND == RK_DHT) {
         out[0] = V0 * p.f; out[N] = VN * p.f;
@@ -371,9 +381,11 @@ fft_r2r_row_kernel(const RowR2RParams<T> p) {
         }
       }
     } else {
-      const C a = sm[A::at(k, w)];
-      const C b = sm[A::at(N - k, w)];
-      const C wk = __ldg(p.rtw + k);
+      const C a = v[q];
+      const C b = half[N - k];
+      // DCT/DST: one table read, exp(-2 pi i k/n) and D(N-k) derived; DHT has no D table
+      const C dk = (KIND == RK_DHT) ? mk<T>(0, 0) : __ldg(p.dtw + k);
+      const C wk = (KIND == RK_DHT) ? __ldg(p.rtw + k) : dct_tw_pow4(dk);
       const C ev = mk<T>((a.x + b.x) * hf, (a.y - b.y) * hf);
       const C df = mk<T>((a.x - b.x) * hf, (a.y + b.y) * hf);
       C od = cmul(df, wk);
@@ -384,8 +396,8 @@ fft_r2r_row_kernel(const RowR2RParams<T> p) {
         out[k] = (Vk.x - Vk.y) * p.f;     out[n - k] = (Vk.x + Vk.y) * p.f;
         out[N - k] = (Vm.x - Vm.y) * p.f; out[N + k] = (Vm.x + Vm.y) * p.f;
       } else {
-        const C uk = cmul(Vk, __ldg(p.dtw + k));
-        const C um = cmul(Vm, __ldg(p.dtw + (N - k)));
+        const C uk = cmul(Vk, dk);
+        const C um = cmul(Vm, dct_tw_nmk(dk));
         if (KIND == RK_DCT) {
           out[k] = uk.x * p.f;     out[n - k] = -uk.y * p.f;
           out[N - k] = um.x * p.f; out[N + k] = -um.y * p.f;

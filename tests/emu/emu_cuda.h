@@ -32,6 +32,7 @@ struct dim3 {
 };
 struct double2 { double x, y; } __attribute__((aligned(16)));
 struct float2 { float x, y; } __attribute__((aligned(8)));
+struct float4 { float x, y, z, w; } __attribute__((aligned(16)));
 static inline double2 make_double2(double a, double b) { double2 r; r.x = a; r.y = b; return r; }
 static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
 template <class T> static inline T __ldg(const T* p) { return *p; }

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 import parity_cases as pc
+from oracle import jt_oracle as o
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 EMU_LIB = os.path.join(HERE, "emu", "_build", "libjtb200_emu.so")
@@ -204,6 +205,37 @@ def test_fast2_r2r(jt, kind, dims):
 @pytest.mark.parametrize("dims", [(8192,), (8192, 32)])
 def test_fast2_r2r_long(jt, dims):
     pc.r2r(jt, "Double", "DCT", dims)
+
+
+# fused inverse kernels and the single-pass column kernels (jtb_r2r_inv.cuh): every length class
+@pytest.mark.parametrize("kind", ["DCT", "DST", "DHT"])
+@pytest.mark.parametrize("prec,dims", [("Double", (64, 64)), ("Double", (256, 32)), ("Double", (128, 48)), ("Double", (1024, 16)),
+                                       ("Float", (64, 32)), ("Float", (512, 32)), ("Double", (32, 32, 32)),
+                                       ("Double", (2048, 64))])
+def test_r2r_single_pass_columns_and_inverse(jt, kind, prec, dims):
+    pc.r2r(jt, prec, kind, dims)
+
+
+def test_r2r_fast_inverse_is_taken(jt):
+    """the inverse of a fused size is one launch per axis (rows) / one or two (columns), not the staged pipeline"""
+    from jtransforms_b200 import _lib
+    L = _lib.get()
+    x = o.fill_uniform(256 * 64, seed=9, lo=-1.0, hi=1.0)
+    t = jt.DoubleDCT_2D(256, 64)
+    a = x.copy()
+    c0 = L.jtb_launch_count(0)
+    t.inverse(a, True)
+    assert L.jtb_launch_count(0) - c0 == 2
+    assert o.rel_l2(a, o.dct_inverse_nd(x, (256, 64), True)) < 1e-12 * 14
+    c0 = L.jtb_launch_count(0)
+    t.forward(a, True)
+    assert L.jtb_launch_count(0) - c0 == 2
+    assert o.rel_l2(a, x) < 1e-12 * 14
+
+
+def test_fft2d_2048_rows_two_pass_columns(jt):
+    """2048-point strided lines: 64 x 32 two-pass split"""
+    pc.fftnd_complex(jt, "Double", (2048, 32))
 
 
 def test_fast2_r2r_strips_and_float(jt, monkeypatch):

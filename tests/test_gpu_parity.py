@@ -153,6 +153,32 @@ def test_r2r_fused_paths(jt, kind, dims):
     pc.r2r(jt, "Double", kind, dims)
 
 
+@pytest.mark.parametrize("kind", ["DCT", "DST", "DHT"])
+@pytest.mark.parametrize("prec,dims", [("Double", (64, 64)), ("Double", (512, 512)), ("Double", (1024, 1024)), ("Double", (128, 48)),
+                                       ("Double", (2048, 2048)), ("Float", (1024, 1024)), ("Float", (256, 64)),
+                                       ("Double", (64, 64, 64)), ("Double", (32, 256, 128)), ("Double", (16384, 64))])
+def test_r2r_single_pass_columns_and_inverse(jt, kind, prec, dims):
+    """fused inverse kernels + single-pass column kernels (jtb_r2r_inv.cuh)"""
+    pc.r2r(jt, prec, kind, dims)
+
+
+def test_r2r_fast_inverse_is_taken(jt):
+    from jtransforms_b200 import _lib
+    L = _lib.get()
+    for dims, want in (((1024, 1024), 2), ((8192, 8192), 3)):
+        n = dims[0] * dims[1]
+        x = o.fill_uniform(n, seed=9, lo=-1.0, hi=1.0)
+        t = jt.DoubleDCT_2D(*dims)
+        a = x.copy()
+        t.inverse(a, True)          # first call builds tables
+        a = x.copy()
+        c0 = L.jtb_launch_count(0)
+        t.inverse(a, True)
+        assert L.jtb_launch_count(0) - c0 == want
+        t.forward(a, True)
+        assert o.rel_l2(a, x) < 1e-12 * 26
+
+
 def test_dct2d_8192(jt):
     """config 4 at full size (DCT; DST/DHT share every kernel and are covered at 2048x1024 above)"""
     import scipy.fft as sfft
