@@ -117,6 +117,8 @@ int fast_r2r_cols(Engine<T>& e, T* a, i64 n, i64 Cn, i64 batches, i64 bdist, int
 template <typename T>
 int fast_r2r_rows_inv(Engine<T>& e, T* a, i64 dist, i64 nlines, i64 n, int kind, T f0, T f, bool* handled);   // jtb_r2r_inv.cu
 template <typename T>
+int fast_rfft_inv(Engine<T>& e, cx<T>* a, i64 dist, i64 nlines, int logN, bool has_scale, T scale, bool* handled);   // jtb_r2r_inv.cu
+template <typename T>
 int fast_r2r_cols_single(Engine<T>& e, T* a, i64 n, i64 Cn, i64 batches, i64 bdist, int kind, bool inverse, T f0, T f,
                          bool* handled);
 template <typename T>

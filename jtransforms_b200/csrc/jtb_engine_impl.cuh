@@ -453,6 +453,11 @@ template <typename T> int Engine<T>::real_inverse_lines(T* a, const Geo& g, i64 
   if (is_pow2(n) && n >= 4 && ilog2(n) - 1 <= max_logn_contig() && geo_even<T>(g) && ((uintptr_t)a % sizeof(C)) == 0) {
     // unscaled power-of-two result is (n/2) x (fft/DoubleFFT_1D.java:946-967)
     const Geo gc = geo_halve(g);
+    if (gc.c[0] == 1 && gc.c[1] == 1 && gc.c[2] == 1) {
+      bool handled = false;
+      JTB_TRY(fast_rfft_inv<T>(*this, (C*)a, gc.d[3], nlines, ilog2(n) - 1, scale, (T)(1.0 / (double)(n / 2)), &handled));
+      if (handled) return ST_OK;
+    }
     Fuse<T> f;
     f.swap_out = 1;
     f.has_scale = scale; f.scale = (T)(1.0 / (double)(n / 2));

@@ -127,6 +127,35 @@ template <> std::vector<ColEntry<float>>& colreg<float>() {
   return r;
 }
 
+// realInverse rows
+template <typename T> struct RfftInvEntry {
+  int logn, loge, W, threads, smem;
+  void (*kern)(const RfftInvParams<T>);
+  unsigned attr_done;
+};
+template <typename T, int LOGN, int LOGE, int W> RfftInvEntry<T> mkrinv() {
+  typedef Sched<LOGN, LOGE> S;
+  RfftInvEntry<T> e;
+  e.logn = LOGN; e.loge = LOGE; e.W = W; e.threads = W * S::TPL;
+  e.smem = (int)((FastAddr<T, S, false, W>::TILE + FastTw<S>::COUNT_SM) * sizeof(cx<T>));
+  e.kern = fft_rfft_inv_row_kernel<T, LOGN, LOGE, W>;
+  e.attr_done = 0;
+  return e;
+}
+template <typename T> std::vector<RfftInvEntry<T>>& rinvreg();
+template <> std::vector<RfftInvEntry<double>>& rinvreg<double>() {
+  static std::vector<RfftInvEntry<double>> r = {mkrinv<double, 5, 3, 32>(), mkrinv<double, 6, 3, 16>(), mkrinv<double, 7, 4, 16>(),
+                                                mkrinv<double, 8, 4, 8>(),  mkrinv<double, 9, 3, 4>(),  mkrinv<double, 10, 3, 2>(),
+                                                mkrinv<double, 11, 3, 1>(), mkrinv<double, 12, 4, 1>()};
+  return r;
+}
+template <> std::vector<RfftInvEntry<float>>& rinvreg<float>() {
+  static std::vector<RfftInvEntry<float>> r = {mkrinv<float, 5, 3, 32>(), mkrinv<float, 6, 3, 32>(), mkrinv<float, 7, 4, 16>(),
+                                               mkrinv<float, 8, 4, 16>(), mkrinv<float, 9, 3, 8>(),  mkrinv<float, 10, 4, 4>(),
+                                               mkrinv<float, 11, 4, 2>(), mkrinv<float, 12, 4, 1>()};
+  return r;
+}
+
 template <typename E> int set_smem_once(E* f, int device) {
   if (!(f->attr_done & (1u << (device & 31)))) {
     JTB_CUDA(cudaFuncSetAttribute(f->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, f->smem));
@@ -166,6 +195,32 @@ int fast_r2r_rows_inv(Engine<T>& e, T* a, i64 dist, i64 nlines, i64 n, int kind,
   *handled = true;
   return ST_OK;
 }
+
+// realInverse of contiguous packed lines (N = 2^logN complex slots per line, line l at l*dist complex), in place
+template <typename T>
+int fast_rfft_inv(Engine<T>& e, cx<T>* a, i64 dist, i64 nlines, int logN, bool has_scale, T scale, bool* handled) {
+  *handled = false;
+  static const bool off = getenv("JTB_NO_RFFTINV") != nullptr;
+  if (g_inv_off || off || nlines <= 0) return ST_OK;
+  RfftInvEntry<T>* r = nullptr;
+  for (auto& x : rinvreg<T>()) if (x.logn == logN) { r = &x; break; }
+  if (!r) return ST_OK;
+  JTB_TRY(set_smem_once(r, e.ctx->device));
+  RfftInvParams<T> p;
+  p.a = a; p.nlines = nlines; p.dist = dist; p.has_scale = has_scale; p.scale = scale;
+  JTB_TRY(fast_stage_table<T>(e, logN, r->loge, &p.twg));
+  const cx<T>* tw[JTB_MAX_STAGES];
+  JTB_TRY(e.tile_tables(logN, tw, &p.rtw));
+  const i64 nblk = (nlines + r->W - 1) / r->W;
+  if (nblk > 0x7fffffffLL) return ST_OK;
+  JTB_LAUNCH(r->kern, (unsigned)nblk, (unsigned)r->threads, (size_t)r->smem, e.st, p);
+  JTB_CUDA(cudaGetLastError());
+  e.ctx->launches++;
+  *handled = true;
+  return ST_OK;
+}
+template int fast_rfft_inv<double>(Engine<double>&, double2*, i64, i64, int, bool, double, bool*);
+template int fast_rfft_inv<float>(Engine<float>&, float2*, i64, i64, int, bool, float, bool*);
 
 // forward or inverse DCT/DST (forward DHT) along the strided axis of length n <= 1024 in ONE pass (fft_col_r2r_kernel)
 template <typename T>

@@ -282,4 +282,77 @@ fft_col_r2r_kernel(const ColR2RParams<T> p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// realInverse of contiguous lines of 2N reals held as the packed half spectrum (N complex slots: slot 0 =
+// (Re X[0], Re X[N]), slot k = X[k]), in place: rftbsub + cftbsub of fft/DoubleFFT_1D.java:946-967 in one kernel.
+//   Z[k] = (X[k] + conj X[N-k])/2 + i e^{+2 pi i k/2N} (X[k] - conj X[N-k])/2,   z = IDFT_N(Z) = x[2j] + i x[2j+1]
+// (unnormalised: N x = (n/2) x, the reference's unscaled power-of-two result).  Thread k builds Z[k] (kept) and
+// Z[N-k] (handed to the owner of the upper half); the result is stored straight from registers.
+template <typename T> struct RfftInvParams {
+  cx<T>* a;
+  i64 nlines, dist;     // lines, distance between lines in complex units
+  int has_scale;
+  T scale;
+  const cx<T>* twg;
+  const cx<T>* rtw;     // exp(-2 pi i k / 2N), k <= N/2
+};
+
+template <typename T, int LOGN, int LOGE, int W>
+__global__ void __launch_bounds__(W * Sched<LOGN, LOGE>::TPL, (Sched<LOGN, LOGE>::E <= 8 ? FastOcc<W * Sched<LOGN, LOGE>::TPL>::MINB
+                                                                                      : (FastOcc<W * Sched<LOGN, LOGE>::TPL>::MINB + 1) / 2))
+fft_rfft_inv_row_kernel(const RfftInvParams<T> p) {
+  typedef Sched<LOGN, LOGE> S;
+  typedef cx<T> C;
+  typedef FastAddr<T, S, false, W> A;
+  constexpr int N = S::N, H = S::E / 2;
+  JTB_DYN_SMEM(smem_raw);
+  C* sm = reinterpret_cast<C*>(smem_raw);
+  C* twt = sm + A::TILE;
+  const int tid = threadIdx.x;
+  const int t = tid % S::TPL, w = tid / S::TPL;
+  for (int i = tid; i < FastTw<S>::COUNT_SM; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
+  const i64 line0 = (i64)blockIdx.x * W;
+  const bool valid = line0 + w < p.nlines;
+  C* cl = p.a + (valid ? (line0 + w) * p.dist : 0);
+  C* half = sm + w * N;
+  C xa[H], xb[H];
+#pragma unroll
+  for (int q = 0; q < H; ++q) {
+    const int k = t + q * S::TPL;
+    xa[q] = valid ? cl[k] : mk<T>(0, 0);
+    xb[q] = valid ? cl[k == 0 ? N / 2 : N - k] : mk<T>(0, 0);
+  }
+  C v[S::E];
+  const T hf = (T)0.5;
+#pragma unroll
+  for (int q = 0; q < H; ++q) {
+    const int k = t + q * S::TPL;
+    const C a = xa[q], b = xb[q];
+    if (k == 0) {
+      v[q] = cswap(mk<T>((a.x + a.y) * hf, (a.x - a.y) * hf));      // Z[0] from (Re X[0], Re X[N])
+      half[N / 2] = cswap(mk<T>(b.x, -b.y));                         // Z[N/2] = conj X[N/2]
+    } else {
+      const C wk = __ldg(p.rtw + k);
+      const C ev = mk<T>((a.x + b.x) * hf, (a.y - b.y) * hf);        // (a + conj b)/2
+      const C df = mk<T>((a.x - b.x) * hf, (a.y + b.y) * hf);        // (a - conj b)/2
+      C od = cmulc(df, wk);
+      od = mk<T>(-od.y, od.x);                                       // * i
+      v[q] = cswap(cadd(ev, od));                                    // Z[k]
+      half[N - k] = cswap(mk<T>(ev.x - od.x, -(ev.y - od.y)));       // Z[N-k] = conj(ev - od)
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = H; q < S::E; ++q) v[q] = half[t + q * S::TPL];
+  __syncthreads();
+  FastLoop<T, S, 0, false, W>::run(v, sm, twt, t, w, p.twg);
+  if (!valid) return;
+#pragma unroll
+  for (int q = 0; q < S::E; ++q) {
+    C z = cswap(v[q]);
+    if (p.has_scale) { z.x *= p.scale; z.y *= p.scale; }
+    cl[t + q * S::TPL] = z;
+  }
+}
+
 }  // namespace jtb
