@@ -7,6 +7,7 @@
 //   3-D complex  fft/DoubleFFT_3D.java:145-325 (xdft3da_subth2 :5505, cdft3db_subth :6318)
 //   3-D real     fft/DoubleFFT_3D.java:1339-1355 (rdft3d_sub :6909-7021)
 //   DCT/DST/DHT  dct/DoubleDCT_2D.java:104-183, dht/DoubleDHT_2D.java:102-190 (+ yTransform :1288-1309)
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/jtb200.h"
@@ -261,8 +262,48 @@ int jtb_exec_batch(jtb_plan* p, int op, void* host_a, int64_t offa, int64_t howm
   Ctx* c = p->ctx;
   std::lock_guard<std::mutex> lk(c->mu);
   JTB_CUDA(cudaSetDevice(p->device));
-  JTB_TRY(c->ensure(c->io, (size_t)span * esz));
   char* h = (char*)host_a + (size_t)offa * esz;
+  // Large batches run as a three-stage pipeline over chunks of whole transforms: H2D of chunk i+1, the kernels of
+  // chunk i and D2H of chunk i-1 overlap (PCIe is full duplex), and the device copy is three chunks instead of the
+  // whole span -- the chunked staging of SURVEY.md 8(f) rank 4.
+  {
+    const char* emb = getenv("JTB_BATCH_MB");   // chunk size of the pipelined path in MiB; 0 disables it
+    const double chunk_mb = emb ? atof(emb) : 64.0;   // measured: 2 GB batch e2e 83.9 ms unpipelined, 53.2 ms at 256 MiB, 46.1 ms at 64 MiB
+    const size_t per = (size_t)dist * esz;
+    i64 nb = per ? (i64)(chunk_mb * 1048576.0 / (double)per) : howmany;
+    if (nb < 1) nb = 1;
+    if (chunk_mb > 0 && howmany > 1 && howmany >= 3 * nb) {
+      JTB_TRY(c->ensure_pipeline());
+      const size_t chunk_elems = (size_t)((nb - 1) * dist + elems);
+      const size_t chunk_bytes = (chunk_elems * esz + 255) / 256 * 256;
+      JTB_TRY(c->ensure(c->io, 3 * chunk_bytes));
+      int s = ST_OK;
+      i64 idx = 0;
+      for (i64 b0 = 0; b0 < howmany && s == ST_OK; b0 += nb, ++idx) {
+        const i64 cnt = howmany - b0 < nb ? howmany - b0 : nb;
+        const int slot = (int)(idx % 3);
+        char* dev = (char*)c->io.p + (size_t)slot * chunk_bytes;
+        char* hb = h + (size_t)b0 * per;
+        const size_t bytes = (size_t)((cnt - 1) * dist + elems) * esz;
+        if (idx >= 3) JTB_CUDA(cudaStreamWaitEvent(c->s_in, c->ev_out[slot], 0));   // slot's previous result is back
+        JTB_CUDA(cudaMemcpyAsync(dev, hb, bytes, cudaMemcpyHostToDevice, c->s_in));
+        JTB_CUDA(cudaEventRecord(c->ev_in[slot], c->s_in));
+        JTB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in[slot], 0));
+        s = p->prec == JTB_F64 ? run_device<double>(p, op, (double*)dev, cnt, dist, scale != 0, c->stream)
+                               : run_device<float>(p, op, (float*)dev, cnt, dist, scale != 0, c->stream);
+        if (s != ST_OK) break;
+        JTB_CUDA(cudaEventRecord(c->ev_c[slot], c->stream));
+        JTB_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_c[slot], 0));
+        JTB_CUDA(cudaMemcpyAsync(hb, dev, bytes, cudaMemcpyDeviceToHost, c->s_out));
+        JTB_CUDA(cudaEventRecord(c->ev_out[slot], c->s_out));
+      }
+      cudaStreamSynchronize(c->s_in);
+      cudaStreamSynchronize(c->stream);
+      JTB_CUDA(cudaStreamSynchronize(c->s_out));
+      return s;
+    }
+  }
+  JTB_TRY(c->ensure(c->io, (size_t)span * esz));
   JTB_CUDA(cudaMemcpyAsync(c->io.p, h, (size_t)in_span * esz, cudaMemcpyHostToDevice, c->stream));
   int s = p->prec == JTB_F64 ? run_device<double>(p, op, (double*)c->io.p, howmany, dist, scale != 0, c->stream)
                              : run_device<float>(p, op, (float*)c->io.p, howmany, dist, scale != 0, c->stream);

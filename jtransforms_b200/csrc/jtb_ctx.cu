@@ -47,6 +47,18 @@ int Ctx::ensure(DevBuf& b, size_t bytes) {
   return ST_OK;
 }
 
+int Ctx::ensure_pipeline() {
+  if (s_in) return ST_OK;
+  JTB_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+  JTB_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 3; ++i) {
+    JTB_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+    JTB_CUDA(cudaEventCreateWithFlags(&ev_c[i], cudaEventDisableTiming));
+    JTB_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+  }
+  return ST_OK;
+}
+
 int Ctx::put_table(const std::string& key, const void* host, size_t bytes, void** dev_out) {
   void* d = nullptr;
   JTB_CUDA(cudaMalloc(&d, bytes < 16 ? 16 : bytes));

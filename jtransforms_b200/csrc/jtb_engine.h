@@ -46,6 +46,9 @@ struct Ctx {
   std::mutex mu;
   DevBuf work[WK_COUNT];
   DevBuf io;                           // device copy of the caller's host array
+  cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined batch path (created on first use)
+  cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_c[3] = {nullptr, nullptr, nullptr}, ev_out[3] = {nullptr, nullptr, nullptr};
+  int ensure_pipeline();
   std::map<std::string, void*> tables; // device tables keyed by name
   size_t work_cap = (size_t)8 << 30;   // chunk limit per workspace
   long launches = 0;                   // kernels launched (bench.py reports this)

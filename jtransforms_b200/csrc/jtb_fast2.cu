@@ -41,6 +41,7 @@ template <> std::vector<F2Entry<double>>& reg2<double>() {
       // second pass, strided lines (row permutation only)
       mk2<double, 6, 3, true, FM_PLAIN, 32>(), mk2<double, 7, 4, true, FM_PLAIN, 16>(), mk2<double, 5, 3, true, FM_PLAIN, 32>(),
       // real-forward rows
+      mk2<double, 5, 3, false, FM_RFFT, 32>(), mk2<double, 6, 3, false, FM_RFFT, 16>(), mk2<double, 7, 4, false, FM_RFFT, 16>(),
       mk2<double, 8, 4, false, FM_RFFT, 8>(), mk2<double, 9, 3, false, FM_RFFT, 4>(), mk2<double, 10, 3, false, FM_RFFT, 2>(),
       mk2<double, 11, 3, false, FM_RFFT, 1>(), mk2<double, 12, 3, false, FM_RFFT, 1>(), mk2<double, 11, 4, false, FM_RFFT, 2>(),
   };
@@ -53,7 +54,9 @@ template <> std::vector<F2Entry<float>>& reg2<float>() {
       mk2<float, 5, 3, true, FM_PLAIN, 32>(), mk2<float, 6, 3, true, FM_PLAIN, 32>(), mk2<float, 7, 4, true, FM_PLAIN, 16>(),
       mk2<float, 9, 3, false, FM_TRANSPOSE, 16>(), mk2<float, 10, 4, false, FM_TRANSPOSE, 16>(),
       mk2<float, 11, 4, false, FM_TRANSPOSE, 8>(),
-      mk2<float, 10, 4, false, FM_RFFT, 4>(), mk2<float, 11, 4, false, FM_RFFT, 2>(),
+      mk2<float, 5, 3, false, FM_RFFT, 32>(), mk2<float, 6, 3, false, FM_RFFT, 32>(), mk2<float, 7, 4, false, FM_RFFT, 16>(),
+      mk2<float, 8, 4, false, FM_RFFT, 16>(), mk2<float, 9, 3, false, FM_RFFT, 8>(),
+      mk2<float, 10, 4, false, FM_RFFT, 4>(), mk2<float, 11, 4, false, FM_RFFT, 2>(), mk2<float, 12, 4, false, FM_RFFT, 1>(),
   };
   return r;
 }

@@ -64,6 +64,14 @@ def test_fft1d_bluestein_two_pass(jt, small_limits, n):
     pc.fft1d_real(jt, "Double", n)
 
 
+def test_fft1d_batch_pipelined(jt, monkeypatch):
+    """jtb_exec_batch in chunks (three-slot H2D / kernels / D2H ring): ragged last chunk, padded distance"""
+    monkeypatch.setenv("JTB_BATCH_MB", "0.004")       # 4 KiB chunks: 64-point double transforms -> 4 per chunk
+    pc.fft1d_batch(jt, "Double", 64, 23)
+    pc.fft1d_batch(jt, "Float", 100, 17, pad=6)
+    pc.fft1d_batch(jt, "Double", 31, 40, pad=2)
+
+
 def test_fft1d_batch(jt):
     pc.fft1d_batch(jt, "Double", 64, 5)
     pc.fft1d_batch(jt, "Float", 17, 4, pad=2)

@@ -179,6 +179,14 @@ def test_r2r_fast_inverse_is_taken(jt):
         assert o.rel_l2(a, x) < 1e-12 * 26
 
 
+def test_fft1d_batch_pipelined(jt, monkeypatch):
+    """jtb_exec_batch as a three-stage pipeline over chunks of transforms (default 64 MiB chunks; here 1 MiB)"""
+    monkeypatch.setenv("JTB_BATCH_MB", "1")
+    pc.fft1d_batch(jt, "Double", 4096, 100)           # 64 KiB per transform -> 16 per chunk, ragged tail
+    pc.fft1d_batch(jt, "Float", 1000, 700, pad=6)     # Bluestein-free mixed radix, padded distance
+    pc.fft1d_batch(jt, "Float", 10007, 64)            # prime length (Bluestein) through the ring
+
+
 def test_dct2d_8192(jt):
     """config 4 at full size (DCT; DST/DHT share every kernel and are covered at 2048x1024 above)"""
     import scipy.fft as sfft
