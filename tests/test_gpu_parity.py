@@ -179,6 +179,25 @@ def test_r2r_fast_inverse_is_taken(jt):
         assert o.rel_l2(a, x) < 1e-12 * 26
 
 
+@pytest.mark.parametrize("offa", [1, 2, 3, 4])
+def test_device_tensor_offsets_fall_back_cleanly(jt, offa):
+    """device-resident arrays at offsets that break the 16/32-byte alignment the vectorised row kernels need"""
+    import torch
+    n = 1024
+    x = o.fill_uniform(n + 8, seed=4, lo=-1.0, hi=1.0)
+    for name, fn, want in (
+            ("dct fwd", lambda t: jt.DoubleDCT_1D(n).forward(t, offa, True), lambda v: o.dct_forward_1d(v, True)),
+            ("dct inv", lambda t: jt.DoubleDCT_1D(n).inverse(t, offa, True), lambda v: o.dct_inverse_1d(v, True)),
+            ("dst inv", lambda t: jt.DoubleDST_1D(n).inverse(t, offa, False), lambda v: o.dst_inverse_1d(v, False)),
+            ("real fwd", lambda t: jt.DoubleFFT_1D(n).realForward(t, offa), lambda v: o.real_forward_1d(v, n)),
+            ("real inv", lambda t: jt.DoubleFFT_1D(n).realInverse(t, offa, True), lambda v: o.real_inverse_1d(v, n, True))):
+        t = torch.from_numpy(x.copy()).cuda()
+        fn(t)
+        got = t.cpu().numpy()
+        assert np.array_equal(got[:offa], x[:offa]) and np.array_equal(got[offa + n:], x[offa + n:]), name
+        assert o.rel_l2(got[offa:offa + n], want(x[offa:offa + n])) < 1e-12 * 10, name
+
+
 def test_fft1d_batch_pipelined(jt, monkeypatch):
     """jtb_exec_batch as a three-stage pipeline over chunks of transforms (default 64 MiB chunks; here 1 MiB)"""
     monkeypatch.setenv("JTB_BATCH_MB", "1")
