@@ -477,7 +477,8 @@ template <> BlueReg<float>& bluereg<float>() {
   static BlueReg<float> r = {
       {mk2x<float, 9, 3, 8, FM_TWID, PRE_CHIRP>(), mk2x<float, 10, 4, 16, FM_TWID, PRE_CHIRP>()},
       {mk2x<float, 9, 3, 8, FM_CHIRP_OUT, PRE_NONE>(), mk2x<float, 10, 4, 16, FM_CHIRP_OUT, PRE_NONE>()},
-      {mkconv<float, 10, 3, 4>(), mkconv<float, 11, 3, 2>(), mkconv<float, 12, 3, 1>()}};
+      {mkconv<float, 10, 3, 4>(), mkconv<float, 11, 3, 2>(), mkconv<float, 12, 3, 1>(), mkconv<float, 11, 4, 2>(),
+       mkconv<float, 12, 4, 1>()}};
   return r;
 }
 
@@ -503,9 +504,19 @@ int fast_bluestein_contig(Engine<T>& e, cx<T>* a, i64 dist, i64 nlines, i64 n, b
   BlueReg<T>& br = bluereg<T>();
   F2Entry<T>*fa = nullptr, *fc = nullptr;
   ConvEntry<T>* fb = nullptr;
-  for (size_t i = 0; i < br.first.size() && !fa; ++i)
-    for (auto& m : br.mid)
-      if (br.first[i].logn + m.logn == logM) { fa = &br.first[i]; fc = &br.last[i]; fb = &m; break; }
+  // tuning knobs: JTB_BLUE_SPLIT = index of the first-pass variant to start from, JTB_BLUE_LOGE = radix of the middle pass
+  static const char* esp = getenv("JTB_BLUE_SPLIT");
+  static const char* elg = getenv("JTB_BLUE_LOGE");
+  // measured (4096 x n = 1 000 003, float): 512 x 4096 radix-8 136.4 ms, radix-16 middle pass 121.8 ms,
+  // 1024 x 2048 split 131.5 ms, both 117.0 ms -> float default; double keeps the 512-point first pass
+  const size_t i0 = esp ? (size_t)atoi(esp) % br.first.size() : (sizeof(T) == 4 ? 1 : 0);
+  const int want_loge = elg ? atoi(elg) : (sizeof(T) == 4 ? 4 : 3);
+  for (size_t ii = 0; ii < br.first.size() && !fa; ++ii) {
+    const size_t i = (i0 + ii) % br.first.size();
+    for (int pass = 0; pass < 2 && !fa; ++pass)
+      for (auto& m : br.mid)
+        if (br.first[i].logn + m.logn == logM && (pass == 1 || m.loge == want_loge)) { fa = &br.first[i]; fc = &br.last[i]; fb = &m; break; }
+  }
   if (!fa) return ST_OK;
   const i64 N1 = 1LL << fa->logn, N2 = 1LL << fb->logn;
   if (N2 % fa->W) return ST_OK;
