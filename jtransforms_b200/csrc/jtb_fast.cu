@@ -140,34 +140,8 @@ int fast_c2c(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, int logn, bool in
   }
   const i64 nblk = ((nlines + pick->W - 1) / pick->W + p.reps - 1) / p.reps;
   if (nblk > 0x7fffffffLL) return ST_OK;
-  p.ldhint = 0; p.raster = 1;
-  int cluster = 1;
-#ifndef JTB_EMU
-  if (strided) {
-    // tuning knobs (strided passes): CTAs of a cluster start together, so the 128-byte pieces that
-    // adjacent column groups read from one row reach DRAM close in time; L2::256B asks L2 for the pair in one burst
-    static const char* ec = getenv("JTB_CLUSTER");
-    static const char* eh = getenv("JTB_LDHINT");
-    cluster = ec ? atoi(ec) : 1;
-    p.ldhint = eh ? atoi(eh) : 0;
-    static const char* er2 = getenv("JTB_RASTER");
-    p.raster = er2 ? atoi(er2) : 1;
-    if (p.raster < 1 || nblk % p.raster) p.raster = 1;
-    if (cluster < 1 || cluster > 8 || (cluster & (cluster - 1))) cluster = 1;
-    while (cluster > 1 && nblk % cluster) cluster >>= 1;
-  }
-  if (cluster > 1) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3((unsigned)nblk); cfg.blockDim = dim3((unsigned)pick->threads);
-    cfg.dynamicSmemBytes = (size_t)pick->smem; cfg.stream = e.st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    JTB_CUDA(cudaLaunchKernelEx(&cfg, pick->kern, p));
-  } else
-#endif
+  // Measured and removed (profiles/r01_sweep_cluster.log, r01_sweep_raster.log): cluster launch of adjacent column
+  // groups, ld.global.L2::256B hints and interleaved CTA rasterisation all slow the strided passes down.
   JTB_LAUNCH(pick->kern, (unsigned)nblk, (unsigned)pick->threads, (size_t)pick->smem, e.st, p);
   JTB_CUDA(cudaGetLastError());
   e.ctx->launches++;

@@ -29,29 +29,7 @@ template <typename T> struct FastParams {
   T scale;
   const cx<T>* twg;  // base twiddles, layout below (fast_twiddle_count entries)
   int reps;          // strided layout: consecutive groups of W lines handled by one CTA (TLB / launch amortisation)
-  int ldhint;        // strided layout: 1 = loads carry the L2::256B prefetch hint (the neighbouring CTA's 128 B)
-  int raster;        // strided layout: > 1 = CTA b works on column group (b % raster) * (grid / raster) + b / raster
 };
-
-// 16-byte / 8-byte global load with the L2 256-byte prefetch-size hint: a strided pass reads 128-byte pieces whose
-// neighbours are read by the adjacent CTA a little later; the hint lets L2 fetch both halves with one DRAM burst.
-template <typename C> __device__ __forceinline__ C ld_l2_256(const C* p) {
-#ifdef JTB_EMU
-  return *p;
-#else
-  C r;
-  if (sizeof(C) == 16) {
-    double x, y;
-    asm volatile("ld.global.L2::256B.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "l"(p));
-    r.x = x; r.y = y;
-  } else {
-    float x, y;
-    asm volatile("ld.global.L2::256B.v2.f32 {%0,%1}, [%2];" : "=f"(x), "=f"(y) : "l"(p));
-    r.x = x; r.y = y;
-  }
-  return r;
-#endif
-}
 
 // four consecutive reals with one request: 256-bit LDG/STG for double (sm_100a: ld.global.v4.f64, 32-byte aligned),
 // 128-bit for float.  A 32-byte-strided pair of 16-byte accesses would touch every sector twice.
@@ -214,9 +192,7 @@ fft_fast_kernel(const FastParams<T> p) {
   for (int i = tid; i < FastTw<S>::COUNT_SM; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
 
   for (int rep = 0; rep < (STRIDED ? p.reps : 1); ++rep) {
-    i64 blk = blockIdx.x;
-    if (STRIDED && p.raster > 1) blk = (i64)(blockIdx.x % p.raster) * (gridDim.x / p.raster) + blockIdx.x / p.raster;
-    const i64 line0 = (blk * (STRIDED ? p.reps : 1) + rep) * W;
+    const i64 line0 = ((i64)blockIdx.x * (STRIDED ? p.reps : 1) + rep) * W;
     if (line0 >= p.nlines) break;
     C* base;
     int es;
@@ -232,10 +208,7 @@ fft_fast_kernel(const FastParams<T> p) {
       es = 1;
     }
     C v[S::E];
-    if (STRIDED && p.ldhint) {
-#pragma unroll
-      for (int q = 0; q < S::E; ++q) v[q] = ld_l2_256(base + (t + q * S::TPL) * es);
-    } else if (valid) {
+    if (valid) {
 #pragma unroll
       for (int q = 0; q < S::E; ++q) v[q] = base[(t + q * S::TPL) * es];
     } else {
