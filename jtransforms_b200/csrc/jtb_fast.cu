@@ -263,6 +263,10 @@ int fast_slice2d(Engine<T>& e, cx<T>* a, i64 nslices, i64 N, bool inverse, bool 
   p.counters = sc[dv].p + 1; p.err = sc[dv].p;
   JTB_TRY(fast_stage_table<T>(e, 9, 3, &p.twg));
   p.inverse = inverse; p.has_scale = has_scale; p.scale = scale;
+  {
+    const char* epl = getenv("JTB_SLICE2D_PIPE");
+    p.pipelined = epl ? atoi(epl) : 1;
+  }
   if (peers) {
     p.scatter = 1; p.logRh = ilog2(N / nranks); p.slice0 = (int)(rank * nslices);
     for (int h = 0; h < 8; ++h) p.peer[h] = h < nranks ? (cx<T>*)peers[h] : nullptr;

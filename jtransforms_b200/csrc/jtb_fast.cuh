@@ -309,6 +309,7 @@ template <typename T> struct Slice2DParams {
   int inverse;
   int has_scale; T scale;
   int scatter, logRh, slice0;
+  int pipelined;       // 1: rows of the next slice before the columns of the current one
   cx<T>* peer[8];
 };
 
@@ -330,29 +331,33 @@ __global__ void __launch_bounds__(W * Sched<LOGN, LOGE>::TPL, 2) fft_slice2d_ker
   if (team >= nteams) return;
   const int per = N / p.team;                 // rows (phase A) / columns (phase B) per CTA
   C v[S::E];
-  for (int slice = team; slice < p.nslices; slice += nteams) {
+  // Software-pipelined over slices: a team transforms the rows of its NEXT slice before it waits for the rows of the
+  // current one, so the arrival counter has long been complete when it is polled (no team-barrier stall) and the
+  // column phase still finds the slice in L2 (two slices of 4 MiB per team in flight).
+  auto rows = [&](int slice) {
     C* sl = p.a + (i64)slice * N * N;
-    // ---- phase A: contiguous rows
-    {
-      const int t = tid % S::TPL, w = tid / S::TPL;
-      for (int r0 = rank * per; r0 < (rank + 1) * per; r0 += W) {
-        C* base = sl + (i64)(r0 + w) * N;
+    const int t = tid % S::TPL, w = tid / S::TPL;
+    for (int r0 = rank * per; r0 < (rank + 1) * per; r0 += W) {
+      C* base = sl + (i64)(r0 + w) * N;
 #pragma unroll
-        for (int q = 0; q < S::E; ++q) v[q] = base[t + q * S::TPL];
-        if (p.inverse) {
+      for (int q = 0; q < S::E; ++q) v[q] = base[t + q * S::TPL];
+      if (p.inverse) {
 #pragma unroll
-          for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
-        }
-        FastLoop<T, S, 0, false, W>::run(v, sm, twt, t, w, p.twg);
-#pragma unroll
-        for (int q = 0; q < S::E; ++q) base[t + q * S::TPL] = v[q];   // stays in the swapped domain for phase B
-        __syncthreads();
+        for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
       }
+      FastLoop<T, S, 0, false, W>::run(v, sm, twt, t, w, p.twg);
+#pragma unroll
+      for (int q = 0; q < S::E; ++q) base[t + q * S::TPL] = v[q];   // stays in the swapped domain for the columns
+      __syncthreads();
     }
-    // ---- team barrier: all rows of this slice are written (and visible at L2) before any column is read
+    // arrive: this CTA's rows are written (and visible at L2) before the counter moves
     if (tid == 0) {
       __threadfence();
       atomicAdd(p.counters + slice, 1);
+    }
+  };
+  auto wait_rows = [&](int slice) {
+    if (tid == 0) {
       const long long t0 = clock64();
       while (*((volatile int*)(p.counters + slice)) < p.team) {
         if (clock64() - t0 > 8000000000LL) { *p.err = 1; break; }
@@ -360,38 +365,48 @@ __global__ void __launch_bounds__(W * Sched<LOGN, LOGE>::TPL, 2) fft_slice2d_ker
       __threadfence();
     }
     __syncthreads();
-    // ---- phase B: columns, W adjacent columns per pass
-    {
-      const int w = tid % W, t = tid / W;
-      for (int c0 = rank * per; c0 < (rank + 1) * per; c0 += W) {
-        const C* base = sl + c0 + w;
+  };
+  auto cols = [&](int slice) {
+    C* sl = p.a + (i64)slice * N * N;
+    const int w = tid % W, t = tid / W;
+    for (int c0 = rank * per; c0 < (rank + 1) * per; c0 += W) {
+      const C* base = sl + c0 + w;
 #pragma unroll
-        for (int q = 0; q < S::E; ++q) v[q] = __ldcg(base + (i64)(t + q * S::TPL) * N);
-        FastLoop<T, S, 0, true, W>::run(v, sm, twt, t, w, p.twg);
-        if (p.has_scale) {
+      for (int q = 0; q < S::E; ++q) v[q] = __ldcg(base + (i64)(t + q * S::TPL) * N);
+      FastLoop<T, S, 0, true, W>::run(v, sm, twt, t, w, p.twg);
+      if (p.has_scale) {
 #pragma unroll
-          for (int q = 0; q < S::E; ++q) { v[q].x *= p.scale; v[q].y *= p.scale; }
-        }
-        if (p.inverse) {
-#pragma unroll
-          for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
-        }
-        if (p.scatter) {
-          const int Rh = 1 << p.logRh;
-          const i64 row0 = (i64)(p.slice0 + slice) * Rh;
-#pragma unroll
-          for (int q = 0; q < S::E; ++q) {
-            const int k2 = t + q * S::TPL;
-            p.peer[k2 >> p.logRh][(row0 + (k2 & (Rh - 1))) * N + c0 + w] = v[q];
-          }
-        } else {
-          C* dst = sl + c0 + w;
-#pragma unroll
-          for (int q = 0; q < S::E; ++q) dst[(i64)(t + q * S::TPL) * N] = v[q];
-        }
-        __syncthreads();
+        for (int q = 0; q < S::E; ++q) { v[q].x *= p.scale; v[q].y *= p.scale; }
       }
+      if (p.inverse) {
+#pragma unroll
+        for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
+      }
+      if (p.scatter) {
+        const int Rh = 1 << p.logRh;
+        const i64 row0 = (i64)(p.slice0 + slice) * Rh;
+#pragma unroll
+        for (int q = 0; q < S::E; ++q) {
+          const int k2 = t + q * S::TPL;
+          p.peer[k2 >> p.logRh][(row0 + (k2 & (Rh - 1))) * N + c0 + w] = v[q];
+        }
+      } else {
+        C* dst = sl + c0 + w;
+#pragma unroll
+        for (int q = 0; q < S::E; ++q) dst[(i64)(t + q * S::TPL) * N] = v[q];
+      }
+      __syncthreads();
     }
+  };
+  int slice = team;
+  if (slice < p.nslices) rows(slice);
+  while (slice < p.nslices) {
+    const int next = slice + nteams;
+    if (next < p.nslices && p.pipelined) rows(next);
+    wait_rows(slice);
+    cols(slice);
+    if (next < p.nslices && !p.pipelined) rows(next);
+    slice = next;
   }
 #endif
 }
