@@ -55,7 +55,10 @@ int64_t jtb_plan_elements(const jtb_plan* plan, int op);
 
 /* host array in, host array out (same addresses): H2D, kernels, D2H, synchronised on return */
 int jtb_exec(jtb_plan* plan, int op, void* host_a, int64_t offa, int scale);
-/* `howmany` transforms, transform b starting at host_a[offa + b*dist] */
+/* `howmany` transforms, transform b starting at host_a[offa + b*dist].  Spans of at least three chunks (64 MiB of
+ * transforms each; JTB_BATCH_MB overrides, 0 disables) run as a three-slot ring -- H2D of chunk i+1, the kernels of
+ * chunk i and D2H of chunk i-1 overlap on two copy streams -- so the device copy is three chunks, not the span.
+ * Pinned host memory (jtb_host_alloc) is what makes the copies asynchronous. */
 int jtb_exec_batch(jtb_plan* plan, int op, void* host_a, int64_t offa, int64_t howmany, int64_t dist, int scale);
 /* device-resident: dev_a is a device pointer (16-byte aligned); asynchronous on `stream` (cudaStream_t, may be 0) */
 int jtb_exec_device(jtb_plan* plan, int op, void* dev_a, int64_t howmany, int64_t dist, int scale, void* stream);

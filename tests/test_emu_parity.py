@@ -218,6 +218,7 @@ def test_fast2_r2r_long(jt, dims):
 # fused inverse kernels and the single-pass column kernels (jtb_r2r_inv.cuh): every length class
 @pytest.mark.parametrize("kind", ["DCT", "DST", "DHT"])
 @pytest.mark.parametrize("prec,dims", [("Double", (64, 64)), ("Double", (256, 32)), ("Double", (128, 48)), ("Double", (1024, 16)),
+                                       ("Double", (32, 16)), ("Double", (64, 48)),
                                        ("Float", (64, 32)), ("Float", (512, 32)), ("Double", (32, 32, 32)),
                                        ("Double", (2048, 64))])
 def test_r2r_single_pass_columns_and_inverse(jt, kind, prec, dims):
