@@ -101,10 +101,30 @@ template <typename T> int real_full(Engine<T>& e, T* a, int rank, const i64* d, 
   typedef cx<T> C;
   JTB_TRY(e.ctx->ensure(e.ctx->work[WK_FULL], (size_t)total * sizeof(C)));
   C* wk = (C*)e.ctx->work[WK_FULL].p;
+  unsigned g, b;
+  {
+    // power-of-two sizes: packed real transform at half the work (realForward on a copy), then one expansion sweep
+    // that fills the Hermitian half (the reference: realForward + fillSymmetric, fft/DoubleFFT_2D.java:956-975)
+    bool p2 = total >= 4;
+    for (int k = 0; k < rank; ++k) p2 = p2 && is_pow2(d[k]) && d[k] >= 2;
+    static const bool off = getenv("JTB_NO_FASTFULL") != nullptr;
+    if (p2 && !off) {
+      T* pk = (T*)wk;
+      JTB_CUDA(cudaMemcpyAsync(pk, a, (size_t)total * sizeof(T), cudaMemcpyDeviceToDevice, e.st));
+      JTB_TRY(real_packed(e, pk, rank, d, false, false));
+      const T f = (inverse && scale) ? (T)(1.0 / (double)total) : (T)1;
+      grid_for(total, &g, &b);
+      if (rank == 1) JTB_LAUNCH(k_expand_full_1d<T>, g, b, 0, e.st, pk, (C*)a, d[0], inverse ? 1 : 0, f);
+      else if (rank == 2) JTB_LAUNCH(k_expand_full_2d<T>, g, b, 0, e.st, pk, (C*)a, d[0], d[1], inverse ? 1 : 0, f);
+      else JTB_LAUNCH(k_expand_full_3d<T>, g, b, 0, e.st, pk, (C*)a, d[0], d[1], d[2], inverse ? 1 : 0, f);
+      JTB_CUDA(cudaGetLastError());
+      e.ctx->launches++;
+      return ST_OK;
+    }
+  }
   R2RParams<T> p;
   p.a = a; p.work = wk; p.g = geo_contig(total); p.line_base = 0; p.nlines = 1; p.n = total;
   p.mode = PRE_R2C; p.dst = 0; p.f0 = p.f = (T)1; p.dtw = nullptr;
-  unsigned g, b;
   grid_for(total, &g, &b);
   JTB_LAUNCH(k_r2r_pre<T>, g, b, 0, e.st, p);
   JTB_CUDA(cudaGetLastError());

@@ -200,6 +200,84 @@ template <typename T> __global__ void k_ytransform3d(T* a, i64 S, i64 R, i64 C) 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Packed real spectrum -> full Hermitian spectrum (the role of fillSymmetric, fft/DoubleFFT_2D.java:3877-3992,
+// fft/DoubleFFT_3D.java:7387-7614, after realForward): every thread produces one complex element of the full array
+// from the packed layout (fft/DoubleFFT_2D.java:794-810, fft/DoubleFFT_3D.java:1298-1328) held in `pk`.
+// conj_out: realInverseFull of real data = conj of the forward spectrum (times `f`).
+template <typename T> __device__ __forceinline__ cx<T> half2d(const T* pk, i64 R, i64 C, i64 r, i64 k) {
+  // H(r, k), 0 <= k <= C/2
+  const i64 h = C / 2;
+  if (k > 0 && k < h) return mk<T>(pk[r * C + 2 * k], pk[r * C + 2 * k + 1]);
+  const i64 rm = (R - r) % R;
+  if (r == 0 || 2 * r == R) return mk<T>(pk[r * C + (k == 0 ? 0 : 1)], (T)0);
+  if (k == 0) return 2 * r < R ? mk<T>(pk[r * C], pk[r * C + 1]) : mk<T>(pk[rm * C], -pk[rm * C + 1]);
+  // k == C/2: a[(R-r) C + 1] = Re, a[(R-r) C] = -Im for 0 < r < R/2; conjugate mirror above R/2
+  return 2 * r < R ? mk<T>(pk[rm * C + 1], -pk[rm * C]) : mk<T>(pk[r * C + 1], pk[r * C]);
+}
+
+template <typename T> __global__ void k_expand_full_1d(const T* pk, cx<T>* out, i64 n, int conj_out, T f) {
+  for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (i64)gridDim.x * blockDim.x) {
+    const i64 kk = 2 * k > n ? n - k : k;
+    cx<T> z;
+    if (kk == 0) z = mk<T>(pk[0], (T)0);
+    else if (2 * kk == n) z = mk<T>(pk[1], (T)0);
+    else z = mk<T>(pk[2 * kk], pk[2 * kk + 1]);
+    if ((2 * k > n) != (conj_out != 0)) z.y = -z.y;
+    out[k] = mk<T>(z.x * f, z.y * f);
+  }
+}
+
+template <typename T> __global__ void k_expand_full_2d(const T* pk, cx<T>* out, i64 R, i64 C, int conj_out, T f) {
+  const i64 total = R * C, h = C / 2;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (i64)gridDim.x * blockDim.x) {
+    const i64 r = i / C, c = i - r * C;
+    cx<T> z;
+    bool cj = conj_out != 0;
+    if (c <= h) z = half2d<T>(pk, R, C, r, c);
+    else { z = half2d<T>(pk, R, C, (R - r) % R, C - c); cj = !cj; }
+    if (cj) z.y = -z.y;
+    out[i] = mk<T>(z.x * f, z.y * f);
+  }
+}
+
+template <typename T> __device__ __forceinline__ cx<T> half3d(const T* pk, i64 S, i64 R, i64 C, i64 k1, i64 k2, i64 k3) {
+  // H(k1, k2, k3), 0 <= k3 <= C/2
+  const i64 h = C / 2;
+  auto at = [&](i64 a, i64 b, i64 c) -> T { return pk[(a * R + b) * C + c]; };
+  if (k3 > 0 && k3 < h) return mk<T>(at(k1, k2, 2 * k3), at(k1, k2, 2 * k3 + 1));
+  const i64 m1 = (S - k1) % S, m2 = (R - k2) % R;
+  const bool k2self = (k2 == 0 || 2 * k2 == R), k1self = (k1 == 0 || 2 * k1 == S);
+  if (k3 == 0) {
+    if (!k2self) return 2 * k2 < R ? mk<T>(at(k1, k2, 0), at(k1, k2, 1)) : mk<T>(at(m1, m2, 0), -at(m1, m2, 1));
+    if (k1self) return mk<T>(at(k1, k2, 0), (T)0);
+    return 2 * k1 < S ? mk<T>(at(k1, k2, 0), at(k1, k2, 1)) : mk<T>(at(m1, k2, 0), -at(m1, k2, 1));
+  }
+  // k3 == C/2
+  if (!k2self) {
+    // 0 < k2 < R/2: (P[(S-k1)%S][R-k2][1], -P[..][0]); above R/2 the conjugate of the mirror element
+    if (2 * k2 < R) return mk<T>(at(m1, R - k2, 1), -at(m1, R - k2, 0));
+    return mk<T>(at(k1, k2, 1), at(k1, k2, 0));     // conj H(m1, m2, h) = conj(P[k1][k2][1], -P[k1][k2][0])
+  }
+  if (k1self) return mk<T>(at(k1, k2, 1), (T)0);
+  return 2 * k1 < S ? mk<T>(at(S - k1, k2, 1), -at(S - k1, k2, 0)) : mk<T>(at(k1, k2, 1), at(k1, k2, 0));
+}
+
+template <typename T> __global__ void k_expand_full_3d(const T* pk, cx<T>* out, i64 S, i64 R, i64 C, int conj_out, T f) {
+  const i64 total = S * R * C, h = C / 2;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (i64)gridDim.x * blockDim.x) {
+    const i64 k1 = i / (R * C), rem = i - k1 * R * C;
+    const i64 k2 = rem / C, k3 = rem - k2 * C;
+    cx<T> z;
+    bool cj = conj_out != 0;
+    if (k3 <= h) z = half3d<T>(pk, S, R, C, k1, k2, k3);
+    else { z = half3d<T>(pk, S, R, C, (S - k1) % S, (R - k2) % R, C - k3); cj = !cj; }
+    if (cj) z.y = -z.y;
+    out[i] = mk<T>(z.x * f, z.y * f);
+  }
+}
+
 // counter-based uniform fill: u(i) = (mix64((seed + i) * gamma) >> 11) * 2^-53 (oracle: fill_uniform)
 template <typename T> __global__ void k_fill_uniform(T* a, i64 count, unsigned long long seed, T lo, T hi) {
   for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (i64)gridDim.x * blockDim.x) {

@@ -21,8 +21,13 @@ for prec, dims in [("Double", (1024, 1024)), ("Double", (4096, 4096)), ("Double"
     plan = getattr(jt, "%sFFT_%dD" % (prec, len(dims)))(*dims)
     f = timeit(lambda: plan.realForward(a))
     i = timeit(lambda: plan.realInverse(a, True))
+    full = None
+    if n <= (1 << 27):
+        a2 = torch.rand(2 * n, dtype=a.dtype, device="cuda")
+        full = round(timeit(lambda: plan.realForwardFull(a2)), 4)
+        del a2
     sweep = 2 * n * a.element_size()
-    print(json.dumps({"kind": prec + "FFT real", "dims": dims, "fwd_ms": round(f, 4), "inv_ms": round(i, 4),
+    print(json.dumps({"kind": prec + "FFT real", "dims": dims, "fwd_ms": round(f, 4), "inv_ms": round(i, 4), "full_ms": full,
                       "fwd_gflops": round(2.5 * n * math.log2(n) / f / 1e6, 1),
                       "fwd_sweeps_at_peak": round(f * 1e-3 * 6553.9e9 / sweep, 2), "inv_sweeps_at_peak": round(i * 1e-3 * 6553.9e9 / sweep, 2)}), flush=True)
     del a

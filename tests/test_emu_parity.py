@@ -64,6 +64,30 @@ def test_fft1d_bluestein_two_pass(jt, small_limits, n):
     pc.fft1d_real(jt, "Double", n)
 
 
+@pytest.mark.parametrize("prec", ["Double", "Float"])
+@pytest.mark.parametrize("dims", [(2, 2), (2, 8), (8, 2), (16, 4), (64, 32), (2, 2, 2), (2, 4, 8), (8, 2, 4), (4, 8, 2),
+                                  (8, 16, 32)])
+def test_real_full_packed_plus_expansion(jt, prec, dims):
+    """realForwardFull / realInverseFull of power-of-two sizes: packed transform + Hermitian expansion kernel"""
+    pc.fftnd_real_full(jt, prec, dims)
+
+
+@pytest.mark.parametrize("n", [4, 8, 64, 1024])
+def test_real_full_1d_expansion(jt, n):
+    x = o.fill_uniform(n, seed=3, lo=-1.0, hi=1.0)
+    for inverse in (False, True):
+        a = np.zeros(2 * n)
+        a[:n] = x
+        z = a.copy()
+        if inverse:
+            jt.DoubleFFT_1D(n).realInverseFull(a, True)
+            want = o.real_inverse_full_1d(z, n, True)
+        else:
+            jt.DoubleFFT_1D(n).realForwardFull(a)
+            want = o.real_forward_full_1d(z, n)
+        assert o.rel_l2(a, want) < 1e-12 * 12
+
+
 def test_fft1d_batch_pipelined(jt, monkeypatch):
     """jtb_exec_batch in chunks (three-slot H2D / kernels / D2H ring): ragged last chunk, padded distance"""
     monkeypatch.setenv("JTB_BATCH_MB", "0.004")       # 4 KiB chunks: 64-point double transforms -> 4 per chunk

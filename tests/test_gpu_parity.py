@@ -198,6 +198,12 @@ def test_device_tensor_offsets_fall_back_cleanly(jt, offa):
         assert o.rel_l2(got[offa:offa + n], want(x[offa:offa + n])) < 1e-12 * 10, name
 
 
+@pytest.mark.parametrize("prec,dims", [("Double", (512, 1024)), ("Float", (256, 128)), ("Double", (64, 128, 256)),
+                                       ("Double", (2, 4096)), ("Double", (4096, 2))])
+def test_real_full_packed_plus_expansion(jt, prec, dims):
+    pc.fftnd_real_full(jt, prec, dims)
+
+
 def test_fft1d_batch_pipelined(jt, monkeypatch):
     """jtb_exec_batch as a three-stage pipeline over chunks of transforms (default 64 MiB chunks; here 1 MiB)"""
     monkeypatch.setenv("JTB_BATCH_MB", "1")
