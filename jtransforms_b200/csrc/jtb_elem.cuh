@@ -278,6 +278,35 @@ template <typename T> __global__ void k_expand_full_3d(const T* pk, cx<T>* out, 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Helpers of the three-pass transform for lines beyond the two-pass limit (jtb_engine_impl.cuh, c2c_big_contig):
+// a[k1*N2 + n2] *= W_n^(+-k1*n2) with W_n^m = A[m >> logL] * B[m & (L-1)]  (the twiddle tables of fs_tables)
+template <typename C>
+__global__ void k_big_twiddle(C* a, i64 N1, int logN2, const C* A, const C* B, int logL, int conj_tw) {
+  const i64 total = N1 << logN2, N2m = (1LL << logN2) - 1, Lm = (1LL << logL) - 1;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (i64)gridDim.x * blockDim.x) {
+    const i64 k1 = i >> logN2, n2 = i & N2m;
+    const i64 m = k1 * n2;
+    const C w = cmul(__ldg(A + (m >> logL)), __ldg(B + (m & Lm)));
+    a[i] = conj_tw ? cmulc(a[i], w) : cmul(a[i], w);
+  }
+}
+
+// out[c*R + r] = in[r*Cn + c] through a 32 x 32 shared-memory tile (blockDim = 32 x 8); R, Cn multiples of 32
+template <typename C> __global__ void k_transpose32(const C* in, C* out, i64 R, i64 Cn) {
+  JTB_DYN_SMEM(smem_raw);                      // 32 x 33 elements
+  C (*tile)[33] = reinterpret_cast<C (*)[33]>(smem_raw);
+  const i64 tiles_c = Cn / 32, ntiles = (R / 32) * tiles_c;
+  for (i64 tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
+    const i64 tr = tb / tiles_c, tc = tb - tr * tiles_c;
+    for (int j = threadIdx.y; j < 32; j += 8) tile[j][threadIdx.x] = in[(tr * 32 + j) * Cn + tc * 32 + threadIdx.x];
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) out[(tc * 32 + j) * R + tr * 32 + threadIdx.x] = tile[threadIdx.x][j];
+    __syncthreads();
+  }
+}
+
 // counter-based uniform fill: u(i) = (mix64((seed + i) * gamma) >> 11) * 2^-53 (oracle: fill_uniform)
 template <typename T> __global__ void k_fill_uniform(T* a, i64 count, unsigned long long seed, T lo, T hi) {
   for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (i64)gridDim.x * blockDim.x) {

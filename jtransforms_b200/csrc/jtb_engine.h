@@ -38,7 +38,7 @@ struct DevBuf {
   size_t bytes = 0;
 };
 
-enum { WK_FOURSTEP = 0, WK_BLUE = 1, WK_REAL = 2, WK_FULL = 3, WK_COUNT = 4 };
+enum { WK_FOURSTEP = 0, WK_BLUE = 1, WK_REAL = 2, WK_FULL = 3, WK_BIG = 4, WK_COUNT = 5 };
 
 struct Ctx {
   int device = 0;
@@ -93,6 +93,8 @@ template <typename T> struct Engine {
   int c2c_pow2(const C* in, const Geo& gi, C* out, const Geo& go, i64 l0, i64 l1, int logn, const Fuse<T>& f,
                int pro = PRO_DIRECT, int epi = EPI_DIRECT);
   int tile_call(const C* in, const Geo& gi, C* out, const Geo& go, i64 l0, i64 l1, int logn, TileParams<T>& p);
+  // contiguous in-place lines longer than the two-pass limit: sub-transforms that are themselves two-pass
+  int c2c_big_contig(C* a, i64 dist, i64 l0, i64 l1, int logn, bool inverse, bool has_scale, T scale);
   // any-length in-place c2c on a batch of lines
   int c2c_lines(C* a, const Geo& g, i64 nlines, i64 n, bool inverse, bool has_scale, T scale);
   // real <-> packed half spectrum (1-D rule of fft/DoubleFFT_1D.java), lines of n reals, geometry in REAL units

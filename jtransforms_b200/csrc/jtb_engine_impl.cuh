@@ -259,7 +259,18 @@ int Engine<T>::c2c_pow2(const C* in, const Geo& gi, C* out, const Geo& go, i64 l
     }
     if (handled) return ST_OK;
   }
-  if (logn > 2 * max_logn_contig()) { set_error("length 2^%d exceeds the two-pass limit 2^%d", logn, 2 * max_logn_contig()); return ST_UNSUPPORTED; }
+  // Beyond the reach of the lean two-pass kernels (2^21) the three-pass composition of lean kernels beats the general
+  // two-pass tile path (2^26: 5.0 ms -> see DESIGN.md) and is the only path above 2^26.
+  if (logn > 2 * max_logn_contig() || logn >= 22) {
+    const bool one_level = gi.c[0] == 1 && gi.c[1] == 1 && gi.c[2] == 1;
+    if (contig && in == out && geo_same(gi, go) && one_level && !f.premul && !f.postmul && f.valid_in < 0 &&
+        f.valid_out < 0 && !f.swap_in2 && !f.swap_out1 && f.swap_in == f.swap_out)
+      return c2c_big_contig(out, go.d[3], l0, l1, logn, f.swap_in != 0, f.has_scale != 0, f.scale);
+    if (logn > 2 * max_logn_contig()) {
+      set_error("length 2^%d exceeds the two-pass limit 2^%d", logn, 2 * max_logn_contig());
+      return ST_UNSUPPORTED;
+    }
+  }
   if (gi.c[2] != 1 || go.c[2] != 1) { set_error("geometry too deep for the two-pass transform"); return ST_UNSUPPORTED; }
 
   // n = N1 * N2, input index j = n1*N2 + n2, output index k = k1 + N1*k2
@@ -340,6 +351,42 @@ int Engine<T>::c2c_pow2(const C* in, const Geo& gi, C* out, const Geo& go, i64 l
 template <typename T>
 int fast_c2c(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, int logn, bool inverse, bool has_scale, T scale,
              bool* handled);   // jtb_fast.cu
+
+// Lines beyond the two-pass limit (2^26 double / 2^28 float; the reference reaches them through LargeArray,
+// fft/DoubleFFT_1D.java:280-304): n = N1*N2 with both factors within the two-pass range.  View the line as [N1][N2]:
+// (1) N2 adjacent strided transforms of length N1 in place, (2) twiddle W_n^(k1 n2), (3) N1 contiguous transforms of
+// length N2, (4) transpose to natural order k1 + N1*k2 through the workspace.  Every step reuses the lean kernels.
+template <typename T>
+int Engine<T>::c2c_big_contig(C* a, i64 dist, i64 l0, i64 l1, int logn, bool inverse, bool has_scale, T scale) {
+  const int l2 = logn / 2, l1g = logn - l2;
+  if (l1g > 2 * max_logn_strided() || l2 > 2 * max_logn_contig() || l2 < 5 || l1g < 5) {
+    set_error("length 2^%d exceeds the three-pass limit", logn);
+    return ST_UNSUPPORTED;
+  }
+  const i64 n = 1LL << logn, N1 = 1LL << l1g, N2 = 1LL << l2;
+  const C *fsA, *fsB;
+  int logL;
+  JTB_TRY(fs_tables(logn, &fsA, &fsB, &logL));
+  JTB_TRY(ctx->ensure(ctx->work[WK_BIG], (size_t)n * sizeof(C)));
+  C* wk = (C*)ctx->work[WK_BIG].p;
+  unsigned g, b;
+  for (i64 l = l0; l < l1; ++l) {
+    C* base = a + l * dist;
+    JTB_TRY(c2c_lines(base, geo_make(N2, 1, n, N2), N2, N1, inverse, false, (T)1));
+    grid_for(n, &g, &b);
+    JTB_LAUNCH(k_big_twiddle<C>, g, b, 0, st, base, N1, l2, fsA, fsB, logL, inverse ? 1 : 0);
+    JTB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    JTB_TRY(c2c_lines(base, geo_contig(N2), N1, N2, inverse, has_scale, scale));
+    i64 nt = (N1 / 32) * (N2 / 32);
+    if (nt > 148 * 16) nt = 148 * 16;
+    JTB_LAUNCH(k_transpose32<C>, (unsigned)nt, dim3(32, 8), (size_t)(32 * 33 * sizeof(C)), st, base, wk, N1, N2);
+    JTB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    JTB_CUDA(cudaMemcpyAsync(base, wk, (size_t)n * sizeof(C), cudaMemcpyDeviceToDevice, st));
+  }
+  return ST_OK;
+}
 
 // ---------------------------------------------------------------------------------- any-length c2c
 template <typename T>

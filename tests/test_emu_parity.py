@@ -88,6 +88,15 @@ def test_real_full_1d_expansion(jt, n):
         assert o.rel_l2(a, want) < 1e-12 * 12
 
 
+def test_fft1d_three_pass(jt):
+    """lines beyond the two-pass limit (Engine::c2c_big_contig), exercised at small sizes with the limits forced down"""
+    import sys
+    env = dict(os.environ, JTB_NO_FAST="1", JTB_NO_FAST2="1")
+    r = subprocess.run([sys.executable, os.path.join(HERE, "helpers", "three_pass_emu.py"), EMU_LIB], env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "three-pass ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_fft1d_batch_pipelined(jt, monkeypatch):
     """jtb_exec_batch in chunks (three-slot H2D / kernels / D2H ring): ragged last chunk, padded distance"""
     monkeypatch.setenv("JTB_BATCH_MB", "0.004")       # 4 KiB chunks: 64-point double transforms -> 4 per chunk

@@ -98,6 +98,40 @@ def test_fft3d_real(jt):
     pc.fftnd_real_full(jt, "Float", (6, 10, 12))
 
 
+@pytest.mark.parametrize("prec,logn", [("Double", 22), ("Float", 23), ("Double", 24)])
+def test_fft1d_three_pass_against_oracle(jt, prec, logn):
+    """2^22 .. 2^26: three-pass composition of the lean kernels"""
+    pc.fft1d_complex(jt, prec, 1 << logn)
+
+
+def test_fft1d_2p27_three_pass_properties(jt):
+    """n = 2^27 (2 GiB) is beyond the two-pass limit: three-pass path; Parseval, spot bins, round trip"""
+    import ctypes
+    import torch
+    n = 1 << 27
+    lib = __import__("jtransforms_b200")._lib.get()
+    a = torch.empty(2 * n, dtype=torch.float64, device="cuda:0")
+    assert lib.jtb_fill_uniform_device(0, 0, ctypes.c_void_p(a.data_ptr()), 2 * n, 7, -1.0, 1.0, None) == 0
+    torch.cuda.synchronize()
+    x = a.clone()
+    f = jt.DoubleFFT_1D(n)
+    f.complexForward(a)
+    torch.cuda.synchronize()
+    e_in, e_out = float((x * x).sum()), float((a * a).sum())
+    assert abs(e_out / (n * e_in) - 1.0) < 1e-12
+    xc = torch.view_as_complex(x.view(-1, 2))
+    ac = torch.view_as_complex(a.view(-1, 2))
+    j = torch.arange(n, device="cuda:0", dtype=torch.int64)
+    for k in (0, 1, 12345, n // 2 + 3, n - 1):
+        ph = ((j * k) % n).to(torch.float64) * (-2.0 * np.pi / n)      # exact phase reduction in integers
+        want = torch.sum(xc * torch.polar(torch.ones_like(ph), ph))
+        assert abs(complex(ac[k] - want)) <= 1e-12 * 27 * float(np.sqrt(e_in)) * 10, k
+        del ph
+    f.complexInverse(a, True)
+    torch.cuda.synchronize()
+    assert float(torch.linalg.norm(a - x) / torch.linalg.norm(x)) <= 1e-12 * 27
+
+
 def test_fft3d_512_properties(jt):
     """config 5 at full size, device resident: spot bins against direct sums, Parseval, round trip"""
     import torch
