@@ -114,6 +114,9 @@ int fast_fourstep_contig(Engine<T>& e, const cx<T>* in, i64 in_dist, cx<T>* out,
 template <typename T>
 int fast_fourstep_strided(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, int logn, bool inverse, bool has_scale,
                           T scale, bool* handled);
+template <typename T>
+int fast_threepass_contig(Engine<T>& e, cx<T>* a, i64 dist, i64 l0, i64 l1, int logn, bool inverse, bool has_scale,
+                          T scale, bool* handled);   // jtb_fast2.cu
 template <typename T> int fast_rfft_fwd(Engine<T>& e, cx<T>* a, i64 dist, i64 nlines, int logN, bool* handled);
 template <typename T>
 int fast_r2r_rows(Engine<T>& e, T* a, i64 dist, i64 nlines, i64 n, int kind, T f0, T f, bool* handled);

@@ -246,6 +246,16 @@ int Engine<T>::c2c_pow2(const C* in, const Geo& gi, C* out, const Geo& go, i64 l
   }
   if (pro != PRO_DIRECT || epi != EPI_DIRECT) { set_error("fused real pass needs a single-tile length"); return ST_UNSUPPORTED; }
   {
+    // Beyond the reach of the lean two-pass kernels (2^21) the three-pass composition of lean kernels beats the
+    // general two-pass tile path and is the only path above 2^26 (JTB_THREEPASS_MIN: test knob).
+    static const char* emin = getenv("JTB_THREEPASS_MIN");
+    const int tp_min = emin ? atoi(emin) : 22;
+    const bool one_level = gi.c[0] == 1 && gi.c[1] == 1 && gi.c[2] == 1;
+    if ((logn > 2 * max_logn_contig() || logn >= tp_min) && contig && in == out && geo_same(gi, go) && one_level &&
+        !f.premul && !f.postmul && f.valid_in < 0 && f.valid_out < 0 && !f.swap_in2 && !f.swap_out1 && f.swap_in == f.swap_out)
+      return c2c_big_contig(out, go.d[3], l0, l1, logn, f.swap_in != 0, f.has_scale != 0, f.scale);
+  }
+  {
     // lean two-pass kernels when nothing but the inverse swaps and a scale is fused
     const bool plain = !f.premul && !f.postmul && f.valid_in < 0 && f.valid_out < 0 && !f.swap_in2 && !f.swap_out1;
     const bool one_level_i = gi.c[0] == 1 && gi.c[1] == 1 && gi.c[2] == 1;
@@ -259,17 +269,9 @@ int Engine<T>::c2c_pow2(const C* in, const Geo& gi, C* out, const Geo& go, i64 l
     }
     if (handled) return ST_OK;
   }
-  // Beyond the reach of the lean two-pass kernels (2^21) the three-pass composition of lean kernels beats the general
-  // two-pass tile path (2^26: 5.0 ms -> see DESIGN.md) and is the only path above 2^26.
-  if (logn > 2 * max_logn_contig() || logn >= 22) {
-    const bool one_level = gi.c[0] == 1 && gi.c[1] == 1 && gi.c[2] == 1;
-    if (contig && in == out && geo_same(gi, go) && one_level && !f.premul && !f.postmul && f.valid_in < 0 &&
-        f.valid_out < 0 && !f.swap_in2 && !f.swap_out1 && f.swap_in == f.swap_out)
-      return c2c_big_contig(out, go.d[3], l0, l1, logn, f.swap_in != 0, f.has_scale != 0, f.scale);
-    if (logn > 2 * max_logn_contig()) {
-      set_error("length 2^%d exceeds the two-pass limit 2^%d", logn, 2 * max_logn_contig());
-      return ST_UNSUPPORTED;
-    }
+  if (logn > 2 * max_logn_contig()) {
+    set_error("length 2^%d exceeds the two-pass limit 2^%d", logn, 2 * max_logn_contig());
+    return ST_UNSUPPORTED;
   }
   if (gi.c[2] != 1 || go.c[2] != 1) { set_error("geometry too deep for the two-pass transform"); return ST_UNSUPPORTED; }
 
@@ -358,6 +360,12 @@ int fast_c2c(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, int logn, bool in
 // length N2, (4) transpose to natural order k1 + N1*k2 through the workspace.  Every step reuses the lean kernels.
 template <typename T>
 int Engine<T>::c2c_big_contig(C* a, i64 dist, i64 l0, i64 l1, int logn, bool inverse, bool has_scale, T scale) {
+  {
+    // lean version: three sweeps (strided two-pass sub-transform with the outer twiddle fused, transposing row pass)
+    bool handled = false;
+    JTB_TRY(fast_threepass_contig<T>(*this, a, dist, l0, l1, logn, inverse, has_scale, scale, &handled));
+    if (handled) return ST_OK;
+  }
   const int l2 = logn / 2, l1g = logn - l2;
   if (l1g > 2 * max_logn_strided() || l2 > 2 * max_logn_contig() || l2 < 5 || l1g < 5) {
     set_error("length 2^%d exceeds the three-pass limit", logn);

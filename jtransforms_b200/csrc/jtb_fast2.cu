@@ -227,6 +227,91 @@ int fast_rfft_fwd(Engine<T>& e, cx<T>* a, i64 dist, i64 nlines, int logN, bool* 
   return ST_OK;
 }
 
+// ------------------------------------------------------------------------------------------ three-pass 1-D
+namespace {
+template <typename T, int LOGN, int LOGE, int W> F2Entry<T> mkbig() {
+  typedef Sched<LOGN, LOGE> S;
+  F2Entry<T> e;
+  e.logn = LOGN; e.loge = LOGE; e.sin = 1; e.mode = FM_PLAIN; e.W = W; e.threads = W * S::TPL;
+  e.smem = (int)((FastAddr<T, S, true, W>::TILE + FastTw<S>::COUNT_SM) * sizeof(cx<T>));
+  e.kern = fft_fast2_kernel<T, LOGN, LOGE, true, FM_PLAIN, W, PRE_BIGTW>;
+  e.attr_done = 0; e.min_lines = 0;
+  for (int d = 0; d < 16; ++d) e.twg[d] = nullptr;
+  return e;
+}
+template <typename T> std::vector<F2Entry<T>>& bigreg();
+template <> std::vector<F2Entry<double>>& bigreg<double>() {
+  static std::vector<F2Entry<double>> r = {mkbig<double, 5, 3, 32>(), mkbig<double, 6, 3, 32>(), mkbig<double, 7, 4, 16>()};
+  return r;
+}
+template <> std::vector<F2Entry<float>>& bigreg<float>() {
+  static std::vector<F2Entry<float>> r = {mkbig<float, 5, 3, 32>(), mkbig<float, 6, 3, 32>(), mkbig<float, 7, 4, 16>()};
+  return r;
+}
+}  // namespace
+
+// Contiguous lines of n = N1*N2 points beyond the lean two-pass range, as THREE sweeps: view the line as [N1][N2];
+//   A: strided transforms over the first factor R1 of N1 = R1*R2 with the inner twiddle (a -> work 1),
+//   B: second factor R2, rows back in natural order k1, times the outer twiddle W_n^(k1*n2) (work 1 -> work 2),
+//   C: contiguous transforms of length N2 with the transposed store k1 + N1*k2 (work 2 -> a).
+template <typename T>
+int fast_threepass_contig(Engine<T>& e, cx<T>* a, i64 dist, i64 l0, i64 l1, int logn, bool inverse, bool has_scale,
+                          T scale, bool* handled) {
+  typedef cx<T> C;
+  *handled = false;
+  if (g_fast2_off || l1 <= l0 || getenv("JTB_NO_THREEPASS")) return ST_OK;
+  F2Entry<T>*fa = nullptr, *fb = nullptr, *fc = nullptr;
+  for (int l2 = 11; l2 >= 8 && !fa; --l2) {
+    F2Entry<T>* z = find2<T>(l2, false, FM_TRANSPOSE);
+    if (!z) continue;
+    const int l1g = logn - l2;
+    for (int la = (l1g + 1) / 2; la <= l1g - 5 && !fa; ++la) {
+      F2Entry<T>* x = find2<T>(la, true, FM_TWID);
+      F2Entry<T>* y = nullptr;
+      for (auto& b : bigreg<T>()) if (b.logn == l1g - la) y = &b;
+      if (x && y) { fa = x; fb = y; fc = z; }
+    }
+  }
+  if (!fa) return ST_OK;
+  const i64 n = 1LL << logn, N2 = 1LL << fc->logn, N1 = n >> fc->logn, R1 = 1LL << fa->logn, R2 = 1LL << fb->logn;
+  if (N2 % fa->W || N2 % fb->W || N1 % fc->W || n > (1LL << 30)) return ST_OK;
+  const C *inA, *inB, *bgA, *bgB;
+  int inL, bgL;
+  JTB_TRY(e.fs_tables(ilog2(N1), &inA, &inB, &inL));
+  JTB_TRY(e.fs_tables(logn, &bgA, &bgB, &bgL));
+  JTB_TRY(e.ctx->ensure(e.ctx->work[WK_FOURSTEP], (size_t)n * sizeof(C)));
+  JTB_TRY(e.ctx->ensure(e.ctx->work[WK_BIG], (size_t)n * sizeof(C)));
+  C* w1 = (C*)e.ctx->work[WK_FOURSTEP].p;
+  C* w2 = (C*)e.ctx->work[WK_BIG].p;
+  for (i64 l = l0; l < l1; ++l) {
+    C* base = a + l * dist;
+    Fast2Params<T> p = blank2<T>();
+    p.in = base; p.out = w1;
+    p.nlines = N2 * R2; p.c0 = (int)N2; p.gmod = (int)R2;
+    p.in_gdist = N2; p.in_cdist = 1; p.in_stride = R2 * N2;
+    p.out_gdist = N2; p.out_cdist = 1; p.out_stride = R2 * N2;
+    p.swap_in = inverse;
+    p.fsA = inA; p.fsB = inB; p.fs_logL = inL; p.tw_src = 1;
+    JTB_TRY(launch2(e, fa, p));
+    Fast2Params<T> q = blank2<T>();
+    q.in = w1; q.out = w2;
+    q.nlines = N2 * R1; q.c0 = (int)N2; q.gmod = (int)R1;
+    q.in_gdist = R2 * N2; q.in_cdist = 1; q.in_stride = N2;
+    q.out_gdist = N2; q.out_cdist = 1; q.out_stride = R1 * N2;
+    q.bigA = bgA; q.bigB = bgB; q.big_logL = bgL;
+    JTB_TRY(launch2(e, fb, q));
+    Fast2Params<T> r = blank2<T>();
+    r.in = w2; r.out = base;
+    r.nlines = N1; r.c0 = (int)N1;
+    r.in_gdist = n; r.in_cdist = N2; r.in_stride = 1;
+    r.out_gdist = dist; r.out_cdist = 1; r.out_stride = N1;
+    r.swap_out = inverse; r.has_scale = has_scale; r.scale = scale;
+    JTB_TRY(launch2(e, fc, r));
+  }
+  *handled = true;
+  return ST_OK;
+}
+
 // ------------------------------------------------------------------------------------------ fused DCT/DST/DHT
 namespace {
 template <typename T> struct RowEntry {
@@ -585,6 +670,7 @@ int fast_bluestein_contig(Engine<T>& e, cx<T>* a, i64 dist, i64 nlines, i64 n, b
                                        bool*);                                                                         \
   template int fast_fourstep_strided<T>(Engine<T>&, cx<T>*, const Geo&, i64, int, bool, bool, T, bool*);               \
   template int fast_rfft_fwd<T>(Engine<T>&, cx<T>*, i64, i64, int, bool*);                                             \
+  template int fast_threepass_contig<T>(Engine<T>&, cx<T>*, i64, i64, i64, int, bool, bool, T, bool*);                 \
   template int fast_bluestein_contig<T>(Engine<T>&, cx<T>*, i64, i64, i64, bool, bool, T, bool*);                      \
   template int fast_r2r_rows<T>(Engine<T>&, T*, i64, i64, i64, int, T, T, bool*);                                      \
   template int fast_r2r_cols<T>(Engine<T>&, T*, i64, i64, i64, i64, int, T, T, bool*);

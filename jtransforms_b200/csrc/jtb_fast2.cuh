@@ -41,11 +41,16 @@ template <typename T> struct Fast2Params {
   const cx<T>* chirp;
   i64 out_n;
   int swap_out1;      // FM_CHIRP_OUT: undo the swapped-domain inverse before the chirp multiply
+  // PRE_BIGTW (second pass of the strided sub-transform of a three-pass 1-D transform): the stored element, output row
+  // k1 = (g % gmod) + gmod*j of column c, is multiplied by W_n^(k1*c) = bigA[m >> big_logL] * bigB[m & mask]
+  const cx<T>* bigA;
+  const cx<T>* bigB;
+  int big_logL;
 };
 
 // PRE_UNPERM_* (second pass of a long strided inverse DCT/DST column, jtb_r2r_inv.cuh) act on the STORE: output
 // element m = j*gmod + (g % gmod) goes to row 2m (m < n/2) or 2(n-1-m)+1 of the array, DST negates the odd rows.
-enum { PRE_NONE = 0, PRE_PERM_DCT = 1, PRE_PERM_DST = 2, PRE_CHIRP = 3, PRE_UNPERM_DCT = 4, PRE_UNPERM_DST = 5 };
+enum { PRE_NONE = 0, PRE_PERM_DCT = 1, PRE_PERM_DST = 2, PRE_CHIRP = 3, PRE_UNPERM_DCT = 4, PRE_UNPERM_DST = 5, PRE_BIGTW = 6 };
 
 template <typename T> __device__ __forceinline__ cx<T> fs_tw2(const Fast2Params<T>& p, int m) {
   return cmul(__ldg(p.fsA + (m >> p.fs_logL)), __ldg(p.fsB + (m & ((1 << p.fs_logL) - 1))));
@@ -141,6 +146,17 @@ fft_fast2_kernel(const Fast2Params<T> p) {
       const int idx = p.tw_src ? g_lo : c;
       C tw = fs_tw2(p, idx * t);
       const C ws = fs_tw2(p, idx * S::TPL);
+#pragma unroll
+      for (int q = 0; q < S::E; ++q) {
+        v[q] = cmul(v[q], tw);
+        if (q + 1 < S::E) tw = cmul(tw, ws);
+      }
+    }
+    if (PRE == PRE_BIGTW) {
+      const i64 mask = (1LL << p.big_logL) - 1;
+      const i64 m0 = ((i64)g_lo + (i64)p.gmod * t) * c, ms = (i64)p.gmod * S::TPL * c;
+      C tw = cmul(__ldg(p.bigA + (m0 >> p.big_logL)), __ldg(p.bigB + (m0 & mask)));
+      const C ws = cmul(__ldg(p.bigA + (ms >> p.big_logL)), __ldg(p.bigB + (ms & mask)));
 #pragma unroll
       for (int q = 0; q < S::E; ++q) {
         v[q] = cmul(v[q], tw);

@@ -97,6 +97,15 @@ def test_fft1d_three_pass(jt):
     assert r.returncode == 0 and "three-pass ok" in r.stdout, r.stdout + r.stderr
 
 
+def test_fft1d_three_pass_lean(jt):
+    """fast_threepass_contig: strided two-pass sub-transform with the outer twiddle fused + transposing row pass"""
+    import sys
+    env = dict(os.environ, JTB_THREEPASS_MIN="19")
+    r = subprocess.run([sys.executable, os.path.join(HERE, "helpers", "three_pass_lean_emu.py"), EMU_LIB], env=env,
+                       capture_output=True, text=True, timeout=1800)
+    assert r.returncode == 0 and "three-pass lean ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_fft1d_batch_pipelined(jt, monkeypatch):
     """jtb_exec_batch in chunks (three-slot H2D / kernels / D2H ring): ragged last chunk, padded distance"""
     monkeypatch.setenv("JTB_BATCH_MB", "0.004")       # 4 KiB chunks: 64-point double transforms -> 4 per chunk
