@@ -179,6 +179,28 @@ class SlabFFT3D:
         self._lines(recv, S, Rh * Cn, Rh * Cn, 1, S * Rh * Cn, Rh * Cn)
         return recv
 
+    def inverse(self, b: torch.Tensor, scale: bool = True, work: torch.Tensor | None = None) -> torch.Tensor:
+        """complexInverse of a k2-slabbed spectrum: ``b`` is this rank's [S][Rh][C] block as ``forward`` returns it
+        (transformed in place for the k1 pass); returns the k1-slabbed local slab [Ls][R][C] of the inverse
+        transform (``b`` itself when P == 1).  ``scale`` divides by S*R*C like the reference
+        (fft/DoubleFFT_3D.java:744-760).  The re-slabbing runs as one all-to-all (NCCL on GPUs, gloo on CPU): the
+        send side needs no packing (the block is already ordered by destination rank)."""
+        S, R, Cn, P, Ls, Rh = self.S, self.R, self.Cn, self.P, self.Ls, self.Rh
+        sc = 1.0 / (float(S) * float(R) * float(Cn)) if scale else 1.0
+        if P == 1:
+            self._lines(b, S, R * Cn, R * Cn, 1, S * R * Cn, R * Cn, inverse=True)
+            self._lines(b, R, Cn * S, Cn, 1, R * Cn, Cn, inverse=True)
+            self._lines(b, Cn, S * R, 1, 0, Cn, 1, inverse=True, scale=sc)
+            return b
+        self._lines(b, S, Rh * Cn, Rh * Cn, 1, S * Rh * Cn, Rh * Cn, inverse=True)      # k1: across slices
+        recv = work if work is not None else torch.empty_like(b)
+        dist.all_to_all_single(recv.view(-1), b.view(-1), group=self.group)              # chunk g = slices of rank g
+        # recv is [h][ls][r][c] (source rank h holds rows h*Rh..): reorder to the local slab [ls][h*Rh + r][c]
+        local = recv.view(P, Ls, Rh, 2 * Cn).permute(1, 0, 2, 3).contiguous().view(-1)
+        self._lines(local, R, Cn * Ls, Cn, 1, R * Cn, Cn, inverse=True)                  # k2: columns inside each slice
+        self._lines(local, Cn, Ls * R, 1, 0, Cn, 1, inverse=True, scale=sc)              # k3: contiguous rows
+        return local
+
     def scatter_to_host(self, result: torch.Tensor, host: torch.Tensor):
         """Place this rank's [S][Rh][C] block into the natural-order host array [S][R][C] (strided D2H)."""
         if self.P == 1:

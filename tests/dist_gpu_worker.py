@@ -26,6 +26,12 @@ for mode in ("p2p", "nccl"):
             got = res.cpu().numpy().reshape(S, Rh, 2 * Cn)
             err = o.rel_l2(got, want[:, rank * Rh:(rank + 1) * Rh])
             assert err < 1e-12 * 20, (mode, S, R, Cn, it, err)
+            if it == 0:          # distributed round trip (inverse of the k2-slabbed spectrum)
+                back = f.inverse(res.clone(), True)
+                torch.cuda.synchronize()
+                ref = x.reshape(S, -1)[rank * Ls:(rank + 1) * Ls].ravel()
+                err = o.rel_l2(back.cpu().numpy(), ref)
+                assert err < 1e-12 * 20, ("inverse", mode, S, R, Cn, err)
         f.close()
 dist.barrier()
 dist.destroy_process_group()

@@ -38,6 +38,12 @@ for (S, R, Cn) in [(4, 4, 8), (8, 2, 4), (6, 10, 5)]:
     assert err < 1e-12 * 12, err
     other = slice((1 - rank) * Rh, (2 - rank) * Rh)
     assert not got[:, other].any()
+    # distributed round trip: inverse of the k2-slabbed spectrum gives back this rank's slices
+    for scale in (True, False):
+        back = f.inverse(res.clone(), scale)
+        ref = x.reshape(S, -1)[rank * Ls:(rank + 1) * Ls].ravel() * (1.0 if scale else S * R * Cn)
+        err = o.rel_l2(back.numpy(), ref)
+        assert err < 1e-12 * 12, ("inverse", scale, err)
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
