@@ -309,6 +309,11 @@ fft_conv_kernel(const ConvParams<T> p) {
 // Replaces per line: dct/DoubleDCT_1D.java:169-194 (pre-butterfly, rftbsub, cftbsub, dctsub, scale),
 // dst/DoubleDST_1D.java:96-160, dht/DoubleDHT_1D.java:94-152.
 enum { RK_DCT = 1, RK_DST = 2, RK_DHT = 3 };
+// resident CTAs the radix-16 row kernels are compiled for (256-thread CTAs: 3 needs <= 85 registers)
+#ifndef JTB_ROW_OCC3
+#define JTB_ROW_OCC3 0
+#endif
+template <int THREADS> struct RowOcc16 { static constexpr int V = (JTB_ROW_OCC3 && THREADS == 256) ? 3 : (FastOcc<THREADS>::MINB + 1) / 2; };
 
 template <typename T> struct RowR2RParams {
   T* a;                 // lines of n reals, line l at l*dist, transformed in place
@@ -321,7 +326,7 @@ template <typename T> struct RowR2RParams {
 
 template <typename T, int LOGN, int LOGE, int KIND, int W>
 __global__ void __launch_bounds__(W * Sched<LOGN, LOGE>::TPL, (Sched<LOGN, LOGE>::E <= 8 ? FastOcc<W * Sched<LOGN, LOGE>::TPL>::MINB
-                                                                                      : (FastOcc<W * Sched<LOGN, LOGE>::TPL>::MINB + 1) / 2))
+                                                                                      : RowOcc16<W * Sched<LOGN, LOGE>::TPL>::V))
 fft_r2r_row_kernel(const RowR2RParams<T> p) {
   typedef Sched<LOGN, LOGE> S;
   typedef cx<T> C;

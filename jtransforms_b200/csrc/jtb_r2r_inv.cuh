@@ -18,7 +18,7 @@ namespace jtb {
 // the upper half before the transform, z[N-1-m] to the thread that stores x[4m..4m+3] after it.
 template <typename T, int LOGN, int LOGE, int KIND, int W>
 __global__ void __launch_bounds__(W * Sched<LOGN, LOGE>::TPL, (Sched<LOGN, LOGE>::E <= 8 ? FastOcc<W * Sched<LOGN, LOGE>::TPL>::MINB
-                                                                                      : (FastOcc<W * Sched<LOGN, LOGE>::TPL>::MINB + 1) / 2))
+                                                                                      : RowOcc16<W * Sched<LOGN, LOGE>::TPL>::V))
 fft_r2r_row_inv_kernel(const RowR2RParams<T> p) {
   typedef Sched<LOGN, LOGE> S;
   typedef cx<T> C;
