@@ -68,7 +68,8 @@ def test_fft1d_batch(jt):
 
 
 @pytest.mark.parametrize("prec", ["Double", "Float"])
-@pytest.mark.parametrize("dims", [(2, 2), (64, 128), (100, 120), (1024, 512), (4096, 64), (16, 8192), (311, 64)])
+@pytest.mark.parametrize("dims", [(2, 2), (64, 128), (100, 120), (1024, 512), (4096, 64), (16, 8192), (311, 64), (2048, 128),
+                                  (8192, 32)])
 def test_fft2d_complex(jt, prec, dims):
     pc.fftnd_complex(jt, prec, dims)
 
