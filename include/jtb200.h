@@ -98,6 +98,10 @@ int jtb_peer_free(int device, void* dev_ptr);
 /* pinned host memory for callers that want DMA-speed jtb_exec (Java: off-heap segments / LargeArray storage) */
 int jtb_host_alloc(void** out, int64_t bytes);
 int jtb_host_free(void* p);
+/* page-lock memory the caller already owns (a Java off-heap segment, the storage of a DoubleLargeArray, a numpy
+ * array) so that jtb_exec / jtb_exec_batch copy it at DMA speed; undo with jtb_host_unregister before freeing it */
+int jtb_host_register(void* p, int64_t bytes);
+int jtb_host_unregister(void* p);
 
 /* synthetic input: a[i] = lo + (hi-lo) * u(seed + i), counter-based (bench and parity harness) */
 int jtb_fill_uniform_device(int prec, int device, void* dev_a, int64_t count, uint64_t seed, double lo, double hi,

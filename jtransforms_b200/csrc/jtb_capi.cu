@@ -471,6 +471,17 @@ int jtb_host_free(void* p) {
   return ST_OK;
 }
 
+int jtb_host_register(void* p, int64_t bytes) {
+  if (!p || bytes <= 0) { set_error("bad argument"); return ST_ARG; }
+  if (!get_ctx(0)) return ST_CUDA;
+  JTB_CUDA(cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault));
+  return ST_OK;
+}
+int jtb_host_unregister(void* p) {
+  if (p) JTB_CUDA(cudaHostUnregister(p));
+  return ST_OK;
+}
+
 int jtb_fill_uniform_device(int prec, int device, void* dev_a, int64_t count, uint64_t seed, double lo, double hi,
                             void* stream) {
   Ctx* c = get_ctx(device);

@@ -95,3 +95,27 @@ class ConcurrencyUtils:
     @classmethod
     def getNumberOfThreads(cls) -> int:
         return cls._n
+
+
+class pinned:
+    """Context manager that page-locks a numpy array for the duration of a block (jtb_host_register), so the
+    host-array API copies it at DMA speed -- what a Java caller does once for an off-heap segment / LargeArray::
+
+        with pinned(a):
+            fft.complexForward(a)
+    """
+
+    def __init__(self, a):
+        self.a = a
+
+    def __enter__(self):
+        import ctypes as C
+        from . import _lib
+        _lib.check(_lib.get().jtb_host_register(C.c_void_p(self.a.ctypes.data), self.a.nbytes))
+        return self.a
+
+    def __exit__(self, *exc):
+        import ctypes as C
+        from . import _lib
+        _lib.check(_lib.get().jtb_host_unregister(C.c_void_p(self.a.ctypes.data)))
+        return False

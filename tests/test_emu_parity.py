@@ -106,6 +106,15 @@ def test_fft1d_three_pass_lean(jt):
     assert r.returncode == 0 and "three-pass lean ok" in r.stdout, r.stdout + r.stderr
 
 
+def test_host_register_symbols(jt):
+    from jtransforms_b200.utils import pinned
+    a = o.fill_uniform(128, seed=1)
+    x = a.copy()
+    with pinned(a):
+        jt.DoubleFFT_1D(64).complexForward(a)
+    assert o.rel_l2(a, o.complex_forward_1d(x, 64)) < 1e-12 * 6
+
+
 def test_fft1d_batch_pipelined(jt, monkeypatch):
     """jtb_exec_batch in chunks (three-slot H2D / kernels / D2H ring): ragged last chunk, padded distance"""
     monkeypatch.setenv("JTB_BATCH_MB", "0.004")       # 4 KiB chunks: 64-point double transforms -> 4 per chunk

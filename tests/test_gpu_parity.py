@@ -239,6 +239,18 @@ def test_real_full_packed_plus_expansion(jt, prec, dims):
     pc.fftnd_real_full(jt, prec, dims)
 
 
+def test_host_register_roundtrip(jt):
+    """jtb_host_register / jtb_host_unregister around a caller-owned array (pinned context manager)"""
+    from jtransforms_b200.utils import pinned
+    n = 1 << 18
+    x = o.fill_uniform(2 * n, seed=8, lo=-1.0, hi=1.0)
+    a = x.copy()
+    with pinned(a):
+        jt.DoubleFFT_1D(n).complexForward(a)
+        jt.DoubleFFT_1D(n).complexInverse(a, True)
+    assert o.rel_l2(a, x) < 1e-12 * 18
+
+
 def test_fft1d_batch_pipelined(jt, monkeypatch):
     """jtb_exec_batch as a three-stage pipeline over chunks of transforms (default 64 MiB chunks; here 1 MiB)"""
     monkeypatch.setenv("JTB_BATCH_MB", "1")
