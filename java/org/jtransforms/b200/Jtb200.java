@@ -38,6 +38,30 @@ public final class Jtb200 {
         FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG, JAVA_INT),
         Linker.Option.critical(true));
     private static final MethodHandle LAST_ERROR = h("jtb_last_error", FunctionDescriptor.of(ADDRESS));
+    // int jtb_host_register(void* p, int64_t bytes) / int jtb_host_unregister(void* p): page-lock off-heap storage
+    // (the memory behind a DoubleLargeArray / FloatLargeArray) once so that every later exec copies at DMA speed
+    private static final MethodHandle HOST_REGISTER = h("jtb_host_register", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG));
+    private static final MethodHandle HOST_UNREGISTER = h("jtb_host_unregister", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+
+    /** Page-locks a native segment until the returned handle is closed. */
+    public static AutoCloseable pin(MemorySegment seg) {
+        try {
+            check((int) HOST_REGISTER.invokeExact(seg, seg.byteSize()));
+        } catch (RuntimeException e) {
+            throw e;
+        } catch (Throwable t) {
+            throw new IllegalStateException(t);
+        }
+        return () -> {
+            try {
+                check((int) HOST_UNREGISTER.invokeExact(seg));
+            } catch (RuntimeException e) {
+                throw e;
+            } catch (Throwable t) {
+                throw new IllegalStateException(t);
+            }
+        };
+    }
 
     /** One jtb_plan*: immutable, thread-safe, freed by close() (or a Cleaner registered by the owner). */
     public static final class Plan implements AutoCloseable {
