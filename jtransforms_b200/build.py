@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libjtb200.so")
-UNITS = ["jtb_ctx", "tile_f64", "tile_f32", "jtb_capi", "jtb_fast", "jtb_fast2", "jtb_mixed", "jtb_r2r_inv"]
+UNITS = ["jtb_ctx", "tile_f64", "tile_f32", "jtb_capi", "jtb_fast", "jtb_fast2", "jtb_mixed", "jtb_r2r_inv", "jtb_stage"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

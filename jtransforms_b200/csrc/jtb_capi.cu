@@ -286,6 +286,24 @@ int jtb_exec_batch(jtb_plan* p, int op, void* host_a, int64_t offa, int64_t howm
   // Large batches run as a three-stage pipeline over chunks of whole transforms: H2D of chunk i+1, the kernels of
   // chunk i and D2H of chunk i-1 overlap (PCIe is full duplex), and the device copy is three chunks instead of the
   // whole span -- the chunked staging of SURVEY.md 8(f) rank 4.
+  // Pageable caller memory (Java heap arrays, plain numpy arrays): multi-threaded staging through page-locked bounce
+  // buffers instead of the driver's single-threaded pageable path (jtb_stage.cu); JTB_STAGE=0 disables it.
+  {
+    const char* est = getenv("JTB_STAGE");
+    const char* emin = getenv("JTB_STAGE_MIN_MB");    // smaller arrays stay on the driver's own path (default 32 MiB)
+    const size_t bytes = (size_t)span * esz;
+    const size_t min_bytes = (size_t)((emin ? atof(emin) : 32.0) * 1048576.0);
+    if ((!est || atoi(est) != 0) && bytes >= min_bytes && host_is_pageable(h)) {
+      JTB_TRY(c->ensure_pipeline());
+      JTB_TRY(c->ensure(c->io, bytes));
+      JTB_TRY(staged_copy(p->device, c->io.p, h, (size_t)in_span * esz, true, nullptr));
+      int s = p->prec == JTB_F64 ? run_device<double>(p, op, (double*)c->io.p, howmany, dist, scale != 0, c->stream)
+                                 : run_device<float>(p, op, (float*)c->io.p, howmany, dist, scale != 0, c->stream);
+      if (s != ST_OK) { cudaStreamSynchronize(c->stream); return s; }
+      JTB_CUDA(cudaEventRecord(c->ev_c[0], c->stream));
+      return staged_copy(p->device, c->io.p, h, bytes, false, c->ev_c[0]);
+    }
+  }
   {
     const char* emb = getenv("JTB_BATCH_MB");   // chunk size of the pipelined path in MiB; 0 disables it
     const double chunk_mb = emb ? atof(emb) : 64.0;   // measured: 2 GB batch e2e 83.9 ms unpipelined, 53.2 ms at 256 MiB, 46.1 ms at 64 MiB

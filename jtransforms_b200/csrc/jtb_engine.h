@@ -61,6 +61,8 @@ struct Ctx {
 
 extern int g_limit_contig, g_limit_strided;   // test knobs: force the two-pass path at small sizes (0 = off)
 Ctx* get_ctx(int device);   // creates on first use; nullptr + error on failure
+bool host_is_pageable(const void* p);                                                                   // jtb_stage.cu
+int staged_copy(int device, void* dev, void* host, size_t bytes, bool to_device, cudaEvent_t after);   // jtb_stage.cu
 void grid_for(i64 work_items, unsigned* grid, unsigned* block);
 
 // Fusion options of one power-of-two c2c call (see TileParams)

@@ -55,7 +55,7 @@ static inline void __syncthreads() { pthread_barrier_wait(jtb_emu::g_bar); }
 
 // ---- minimal runtime API -------------------------------------------------
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1, cudaErrorUnknown = 999 };
 typedef struct jtb_emu_stream* cudaStream_t;
 typedef struct jtb_emu_event { double t; }* cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };

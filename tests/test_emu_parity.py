@@ -115,6 +115,17 @@ def test_host_register_symbols(jt):
     assert o.rel_l2(a, o.complex_forward_1d(x, 64)) < 1e-12 * 6
 
 
+def test_staged_pageable_copies(jt, monkeypatch):
+    """pageable caller memory: multi-threaded staging through bounce buffers (jtb_stage.cu), several 8 MiB chunks,
+    ragged tail, real-full op whose input is half of the output span"""
+    monkeypatch.setenv("JTB_EMU_PAGEABLE", "1")
+    monkeypatch.setenv("JTB_STAGE_MIN_MB", "0")
+    monkeypatch.setenv("JTB_STAGE_THREADS", "3")
+    pc.fft1d_batch(jt, "Double", 1024, 1100, pad=2)       # 17.2 MiB -> 3 chunks
+    pc.fft1d_complex(jt, "Double", 64)
+    pc.fftnd_real_full(jt, "Double", (16, 8))
+
+
 def test_fft1d_batch_pipelined(jt, monkeypatch):
     """jtb_exec_batch in chunks (three-slot H2D / kernels / D2H ring): ragged last chunk, padded distance"""
     monkeypatch.setenv("JTB_BATCH_MB", "0.004")       # 4 KiB chunks: 64-point double transforms -> 4 per chunk

@@ -239,6 +239,22 @@ def test_real_full_packed_plus_expansion(jt, prec, dims):
     pc.fftnd_real_full(jt, prec, dims)
 
 
+def test_staged_pageable_copies(jt):
+    """plain (pageable) numpy arrays above 32 MiB go through the multi-threaded staging path; pinned ones do not"""
+    n = 1 << 22                                   # 64 MiB of complex doubles
+    x = o.fill_uniform(2 * n, seed=12, lo=-1.0, hi=1.0)
+    a = x.copy()
+    f = jt.DoubleFFT_1D(n)
+    f.complexForward(a)
+    want = o.complex_forward_1d(x, n)
+    assert o.rel_l2(a, want) < 1e-12 * 22
+    f.complexInverse(a, True)
+    assert o.rel_l2(a, x) < 1e-12 * 22
+    # odd byte count / ragged last chunk, float, real-full (input span = half of the output span)
+    pc.fft1d_batch(jt, "Float", 1000003, 5, pad=2)
+    pc.fftnd_real_full(jt, "Double", (2048, 4096))
+
+
 def test_host_register_roundtrip(jt):
     """jtb_host_register / jtb_host_unregister around a caller-owned array (pinned context manager)"""
     from jtransforms_b200.utils import pinned
