@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -26,7 +27,8 @@ struct StagePool {
   cudaEvent_t ev[kMaxThreads] = {nullptr};
   cudaStream_t stream[kMaxThreads] = {nullptr};
 };
-StagePool g_pool;   // guarded by the context mutex of the (single) device that uses it at a time
+StagePool g_pool;
+std::mutex g_pool_mu;   // one staged copy at a time per process (the pool is rebuilt when the device changes)
 
 int pool_init(int device) {
   if (g_pool.nthreads > 0 && g_pool.device == device) return ST_OK;
@@ -66,6 +68,7 @@ bool host_is_pageable(const void* p) {
 // dev <- host (to_device) or host <- dev, `bytes` long; `after` (may be null) is an event the device side must wait for
 // before the first chunk moves (device -> host: the kernels that produce the data).  Synchronous on return.
 int staged_copy(int device, void* dev, void* host, size_t bytes, bool to_device, cudaEvent_t after) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
   JTB_TRY(pool_init(device));
   const int nt = g_pool.nthreads;
   const size_t nchunks = (bytes + kChunk - 1) / kChunk;
