@@ -80,6 +80,12 @@ int jtb_fft3d_k2_scatter(int prec, int device, const void* local_a, int64_t Ls, 
  * slice_base (lets the caller pipeline the k3 pass of one chunk under the exchange of the previous one) */
 int jtb_fft3d_k2_scatter_chunk(int prec, int device, const void* local_a, int64_t Ls, int64_t slice_base, int64_t R,
                                int64_t C, int nranks, void* const* recv_ptrs, int inverse, void* stream);
+/* The way back (distributed complexInverse): rank h holds the k2-slabbed block [S][Rh][C].  Runs the slice-axis (k1)
+ * pass over it and stores output row k1 straight into the buffer of the GPU that owns slice k1 after re-slabbing over
+ * k1 (peer g = k1/(S/P) receives [k1 % (S/P)][h*Rh + r][c] of its [S/P][R][C] slab): the second all-to-all of a
+ * round trip, fused into the kernel's stores like the first. */
+int jtb_fft3d_k1_scatter(int prec, int device, const void* local_b, int64_t S, int64_t Rh, int64_t C, int nranks,
+                         int rank, void* const* recv_ptrs, int inverse, void* stream);
 /* Both in-slice passes (rows, then columns) of `nslices` rows x cols slices in place; recv_ptrs == NULL keeps the
  * result local, otherwise the column pass stores straight into the peers' receive buffers as
  * jtb_fft3d_k2_scatter does.  512 x 512 double slices run as ONE persistent cooperative kernel that keeps the

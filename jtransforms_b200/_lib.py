@@ -21,7 +21,7 @@ SYMBOLS = [
     "jtb_plan_create", "jtb_plan_destroy", "jtb_plan_elements", "jtb_exec", "jtb_exec_batch", "jtb_exec_device",
     "jtb_lines_c2c_device", "jtb_host_alloc", "jtb_host_free", "jtb_host_register", "jtb_host_unregister", "jtb_fill_uniform_device", "jtb_device_count",
     "jtb_launch_count", "jtb_last_error", "jtb_version", "jtb_debug_set_limits",
-    "jtb_fft3d_k2_scatter", "jtb_fft3d_k2_scatter_chunk", "jtb_fft2d_slices_device", "jtb_peer_barrier", "jtb_peer_alloc", "jtb_peer_open", "jtb_peer_close", "jtb_peer_free",
+    "jtb_fft3d_k2_scatter", "jtb_fft3d_k2_scatter_chunk", "jtb_fft3d_k1_scatter", "jtb_fft2d_slices_device", "jtb_peer_barrier", "jtb_peer_alloc", "jtb_peer_open", "jtb_peer_close", "jtb_peer_free",
 ]
 
 _lib = None
@@ -49,6 +49,7 @@ def _bind(lib):
     lib.jtb_device_count.restype = ci
     lib.jtb_fft3d_k2_scatter.argtypes = [ci, ci, vp, i64, i64, i64, ci, ci, C.POINTER(vp), ci, vp]
     lib.jtb_fft2d_slices_device.argtypes = [ci, ci, vp, i64, i64, i64, ci, ci, C.POINTER(vp), ci, vp]
+    lib.jtb_fft3d_k1_scatter.argtypes = [ci, ci, vp, i64, i64, i64, ci, ci, C.POINTER(vp), ci, vp]
     lib.jtb_fft3d_k2_scatter_chunk.argtypes = [ci, ci, vp, i64, i64, i64, i64, ci, C.POINTER(vp), ci, vp]
     lib.jtb_peer_barrier.argtypes = [ci, C.POINTER(vp), ci, ci, i64, vp]
     lib.jtb_peer_alloc.argtypes = [ci, i64, C.POINTER(vp), C.c_char_p]

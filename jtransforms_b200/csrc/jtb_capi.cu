@@ -425,6 +425,21 @@ int jtb_fft3d_k2_scatter_chunk(int prec, int device, const void* local_a, int64_
   return fast_scatter<float>(e, (const float2*)local_a, Ls, R, Cn, nranks, 0, recv_ptrs, inverse != 0, slice_base);
 }
 
+int jtb_fft3d_k1_scatter(int prec, int device, const void* local_b, int64_t S, int64_t Rh, int64_t Cn, int nranks,
+                         int rank, void* const* recv_ptrs, int inverse, void* stream) {
+  if (!local_b || !recv_ptrs || S < 2 || Rh < 1 || Cn < 1 || rank < 0 || rank >= nranks) { set_error("bad argument"); return ST_ARG; }
+  Ctx* c = get_ctx(device);
+  if (!c) return ST_CUDA;
+  std::lock_guard<std::mutex> lk(c->mu);
+  JTB_CUDA(cudaSetDevice(device));
+  if (prec == JTB_F64) {
+    Engine<double> e(c, (cudaStream_t)stream);
+    return fast_scatter<double>(e, (const double2*)local_b, 1, S, Rh * Cn, nranks, rank, recv_ptrs, inverse != 0, 0, true);
+  }
+  Engine<float> e(c, (cudaStream_t)stream);
+  return fast_scatter<float>(e, (const float2*)local_b, 1, S, Rh * Cn, nranks, rank, recv_ptrs, inverse != 0, 0, true);
+}
+
 int jtb_peer_barrier(int device, void* const* flag_ptrs, int nranks, int rank, int64_t epoch, void* stream) {
   Ctx* c = get_ctx(device);
   if (!c) return ST_CUDA;

@@ -108,7 +108,7 @@ template <typename T> struct Engine {
 
 template <typename T>
 int fast_scatter(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, int nranks, int rank, void* const* peers,
-                 bool inverse, i64 slice_base = -1);   // jtb_fast.cu
+                 bool inverse, i64 slice_base = -1, bool back = false);   // jtb_fast.cu
 template <typename T> int fast_stage_table(Engine<T>& e, int logn, int loge, const cx<T>** out);   // jtb_fast.cu
 template <typename T>
 int fast_fourstep_contig(Engine<T>& e, const cx<T>* in, i64 in_dist, cx<T>* out, i64 out_dist, i64 l0, i64 l1, int logn,

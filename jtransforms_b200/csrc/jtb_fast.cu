@@ -179,7 +179,7 @@ template <> std::vector<ScatterEntry<float>>& scatter_registry<float>() {
 
 template <typename T>
 int fast_scatter(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, int nranks, int rank, void* const* peers,
-                 bool inverse, i64 slice_base) {
+                 bool inverse, i64 slice_base, bool back) {
   if (!is_pow2(R) || nranks < 1 || nranks > 8 || !is_pow2(nranks) || R % nranks) {
     set_error("fused exchange needs power-of-two rows and 1, 2, 4 or 8 ranks");
     return ST_UNSUPPORTED;
@@ -200,6 +200,12 @@ int fast_scatter(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, int nranks
   p.a = a;
   for (int h = 0; h < 8; ++h) p.peer[h] = h < nranks ? (cx<T>*)peers[h] : nullptr;
   p.Ls = (int)Ls; p.C = (int)Cn; p.logRh = ilog2(R / nranks); p.slice0 = slice_base >= 0 ? (int)slice_base : (int)(rank * Ls); p.inverse = inverse;
+  if (back) {   // inverse re-slabbing: one [S][Rh*C] block, output row k1 -> [k1 % Ls][rank*Rh + r][c] of its owner
+    if (Ls != 1) { set_error("internal: the inverse exchange takes the block as one slice"); return ST_ARG; }
+    p.row_base = rank; p.row_ls_mul = 0; p.row_mul = nranks;
+  } else {
+    p.row_base = (long long)p.slice0 * (R / nranks); p.row_ls_mul = (int)(R / nranks); p.row_mul = 1;
+  }
   JTB_TRY(fast_stage_table<T>(e, logn, pick->loge, &p.twg));
   const unsigned nblk = (unsigned)(Ls * (Cn / pick->W));
   JTB_LAUNCH(pick->kern, nblk, (unsigned)pick->threads, (size_t)pick->smem, e.st, p);
@@ -296,8 +302,8 @@ int peer_barrier(Ctx* ctx, cudaStream_t st, void* const* flag_ptrs, int nranks, 
   return ST_OK;
 }
 
-template int fast_scatter<double>(Engine<double>&, const double2*, i64, i64, i64, int, int, void* const*, bool, i64);
-template int fast_scatter<float>(Engine<float>&, const float2*, i64, i64, i64, int, int, void* const*, bool, i64);
+template int fast_scatter<double>(Engine<double>&, const double2*, i64, i64, i64, int, int, void* const*, bool, i64, bool);
+template int fast_scatter<float>(Engine<float>&, const float2*, i64, i64, i64, int, int, void* const*, bool, i64, bool);
 template int fast_c2c<double>(Engine<double>&, double2*, const Geo&, i64, int, bool, bool, double, bool*);
 template int fast_c2c<float>(Engine<float>&, float2*, const Geo&, i64, int, bool, bool, float, bool*);
 

@@ -250,6 +250,12 @@ template <typename T> struct ScatterParams {
   int slice0;         // g * Ls
   int inverse;
   const cx<T>* twg;
+  // destination row of output row k2 of local slice ls inside the owner's buffer:
+  //   row_base + ls*row_ls_mul + (k2 % Rh)*row_mul
+  // forward re-slabbing: (slice0 + ls)*Rh + rl  ->  row_base = slice0*Rh, row_ls_mul = Rh, row_mul = 1;
+  // inverse re-slabbing (one [S][Rh*C] "slice", owner layout [Ls][R][C]): rl*P + g  ->  row_base = g, row_mul = P
+  long long row_base;
+  int row_ls_mul, row_mul;
 };
 
 template <typename T, int LOGN, int LOGE, int W>
@@ -282,13 +288,13 @@ fft_scatter_kernel(const ScatterParams<T> p) {
     for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
   }
   const int Rh = 1 << p.logRh;
-  const i64 row0 = (i64)(p.slice0 + ls) * Rh;
+  const i64 row0 = p.row_base + (i64)ls * p.row_ls_mul;
 #pragma unroll
   for (int q = 0; q < S::E; ++q) {
     const int k2 = t + q * S::TPL;
     const int h = k2 >> p.logRh;
     const int rl = k2 & (Rh - 1);
-    p.peer[h][(row0 + rl) * p.C + c] = v[q];
+    p.peer[h][(row0 + (i64)rl * p.row_mul) * p.C + c] = v[q];
   }
 }
 

@@ -192,6 +192,21 @@ class SlabFFT3D:
             self._lines(b, R, Cn * S, Cn, 1, R * Cn, Cn, inverse=True)
             self._lines(b, Cn, S * R, 1, 0, Cn, 1, inverse=True, scale=sc)
             return b
+        if self.exchange == "p2p" and self._peer is not None and b.is_cuda:
+            # k1 pass whose stores ARE the second all-to-all (peer stores into the owners' [Ls][R][C] slabs)
+            stream = C.c_void_p(torch.cuda.current_stream(b.device).cuda_stream)
+            buf = self.step & 1
+            rc = self.lib.jtb_fft3d_k1_scatter(self.prec, self.dev, C.c_void_p(b.data_ptr()), S, Rh, Cn, P, self.rank,
+                                               self._peer["arr"][buf], 1, stream)
+            if rc == _lib.OK:
+                self.step += 1
+                _lib.check(self.lib.jtb_peer_barrier(self.dev, self._peer["arr"][2], P, self.rank, self.step, stream))
+                local = self._recv_tensor(buf)
+                self._lines(local, R, Cn * Ls, Cn, 1, R * Cn, Cn, inverse=True)
+                self._lines(local, Cn, Ls * R, 1, 0, Cn, 1, inverse=True, scale=sc)
+                return local
+            if rc != _lib.ERR_UNSUPPORTED:      # no fused kernel for this shape is the same answer on every rank
+                _lib.check(rc)
         self._lines(b, S, Rh * Cn, Rh * Cn, 1, S * Rh * Cn, Rh * Cn, inverse=True)      # k1: across slices
         recv = work if work is not None else torch.empty_like(b)
         dist.all_to_all_single(recv.view(-1), b.view(-1), group=self.group)              # chunk g = slices of rank g

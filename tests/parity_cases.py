@@ -215,3 +215,22 @@ def slab_scatter_virtual(lib, prec, dims, P, torch_device="cpu", dev_index=0, fu
                                         S * Rh * Cn, Rh * Cn, 0, 1.0, st()) == 0
         got = recvs[h].cpu().numpy().reshape(S, Rh, 2 * Cn)
         check(got, want[:, h * Rh:(h + 1) * Rh], prec, S * R * Cn, "slab scatter P=%d rank %d" % (P, h))
+    # the way back: fused k1 pass + exchange (jtb_fft3d_k1_scatter) into P slab buffers, then the local k2 / k3 passes
+    backs = [torch.zeros(2 * Ls * R * Cn, dtype=tdt, device=torch_device) for _ in range(P)]
+    barr = (C.c_void_p * P)(*[r.data_ptr() for r in backs])
+    for h in range(P):
+        rc = lib.jtb_fft3d_k1_scatter(pcode, dev_index, C.c_void_p(recvs[h].data_ptr()), S, Rh, Cn, P, h, barr, 1, st())
+        if rc == 2:          # no fused kernel for this slice count
+            assert S not in (64, 512), lib.jtb_last_error()
+            return
+        assert rc == 0, lib.jtb_last_error()
+    sc = 1.0 / (S * R * Cn)
+    for g in range(P):
+        assert lib.jtb_lines_c2c_device(pcode, dev_index, C.c_void_p(backs[g].data_ptr()), R, Cn * Ls, Cn, 1, R * Cn, Cn,
+                                        1, 1.0, st()) == 0
+        assert lib.jtb_lines_c2c_device(pcode, dev_index, C.c_void_p(backs[g].data_ptr()), Cn, Ls * R, 1, 0, Cn, 1, 1, sc,
+                                        st()) == 0
+        # recvs hold the forward spectrum; the three inverse passes with the 1/(S R C) scale give the input back
+        got = backs[g].cpu().numpy()
+        ref = x.astype(np.float64).reshape(S, -1)[g * Ls:(g + 1) * Ls].ravel()
+        check(got, ref, prec, S * R * Cn, "slab round trip P=%d rank %d" % (P, g))

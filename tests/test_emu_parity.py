@@ -224,6 +224,15 @@ def test_fast_kernel_variants(jt, monkeypatch):
         pc.fft1d_batch(jt, "Double", 512, 3, pad=2)
 
 
+@pytest.mark.parametrize("P", [2, 4, 8])
+def test_slab_round_trip_virtual_ranks(jt, P):
+    """64 slices: the way back (jtb_fft3d_k1_scatter, inverse re-slabbing fused into the k1 pass) is exercised too"""
+    from jtransforms_b200 import _lib
+    pc.slab_scatter_virtual(_lib.get(), "Double", (64, 64, 8), P)
+    if P == 2:
+        pc.slab_scatter_virtual(_lib.get(), "Float", (64, 64, 16), P)
+
+
 @pytest.mark.parametrize("P", [1, 2, 4, 8])
 def test_slab_scatter_virtual_ranks(jt, P):
     from jtransforms_b200 import _lib
