@@ -18,6 +18,11 @@
  *   jtb_exec_device   <- same transforms on device-resident data (benchmarks, multi-GPU composition)
  *   jtb_lines_c2c_device <- the strided line loops of the N-D drivers (fft/DoubleFFT_3D.java:5505-5713,
  *                        :6318-6520) exposed so a host layer can run slab-decomposed passes per GPU
+ *   jtb_fft3d_k2_scatter / jtb_fft3d_k1_scatter / jtb_fft2d_slices_device <- the slice-axis gather of cdft3db_subth
+ *                        (fft/DoubleFFT_3D.java:6318-6520) when the slices live on several GPUs: the re-slabbing
+ *                        all-to-all (forward and back) fused into the pass's stores over NVLink peer mappings
+ *   jtb_host_alloc / jtb_host_register <- the role of JLargeArrays' off-heap storage at the boundary
+ *                        (DoubleLargeArray, fft/DoubleFFT_1D.java:280-304): page-locked caller memory
  *
  * All transforms are in place on interleaved (re, im) or real arrays exactly as the reference lays them out.
  * Functions return 0 on success or a JTB_ERR_* code; jtb_last_error() returns the thread-local message.
