@@ -38,5 +38,14 @@ def test_no_cpu_fallback():
     try:
         with pytest.raises(_lib.JtbError, match="no CUDA device|CUDA"):
             jt.DoubleFFT_1D(8).complexForward(np.zeros(16))
+        # the memory and multi-GPU entry points refuse as well (JTB_ERR_CUDA = 3): nothing runs on the host
+        lib = _lib.get()
+        a = np.zeros(64)
+        p = ctypes.c_void_p()
+        assert lib.jtb_host_alloc(ctypes.byref(p), 64) == _lib.ERR_CUDA
+        assert lib.jtb_host_register(ctypes.c_void_p(a.ctypes.data), a.nbytes) == _lib.ERR_CUDA
+        arr = (ctypes.c_void_p * 2)(a.ctypes.data, a.ctypes.data)
+        assert lib.jtb_fft3d_k1_scatter(0, 0, ctypes.c_void_p(a.ctypes.data), 64, 1, 8, 2, 0, arr, 1, None) == _lib.ERR_CUDA
+        assert lib.jtb_lines_c2c_device(0, 0, ctypes.c_void_p(a.ctypes.data), 8, 1, 1, 0, 8, 1, 0, 1.0, None) == _lib.ERR_CUDA
     finally:
         _lib._lib = old
