@@ -21,6 +21,11 @@ SYMBOLS = [
     "jtb_plan_create", "jtb_plan_destroy", "jtb_plan_elements", "jtb_exec", "jtb_exec_batch", "jtb_exec_device",
     "jtb_lines_c2c_device", "jtb_host_alloc", "jtb_host_free", "jtb_host_register", "jtb_host_unregister", "jtb_fill_uniform_device", "jtb_device_count",
     "jtb_launch_count", "jtb_last_error", "jtb_version", "jtb_debug_set_limits",
+    "jtb_debug_table_bytes", "jtb_plan_set_devices", "jtb_plan_device_count", "jtb_exec_n",
+    "jtb_slab_create", "jtb_slab_destroy", "jtb_slab_export", "jtb_slab_connect_ipc", "jtb_slab_connect_local",
+    "jtb_nccl_unique_id", "jtb_slab_nccl_init", "jtb_slab_nccl_init_local", "jtb_slab_set_exchange",
+    "jtb_slab_block_elements", "jtb_slab_forward", "jtb_slab_back", "jtb_slab_group_forward", "jtb_slab_group_back",
+    "jtb_slab_status", "jtb_slab_profile", "jtb_slab_last_times", "jtb_lines_c2c_out_device",
     "jtb_fft3d_k2_scatter", "jtb_fft3d_k2_scatter_chunk", "jtb_fft3d_k1_scatter", "jtb_fft2d_slices_device", "jtb_peer_barrier", "jtb_peer_alloc", "jtb_peer_open", "jtb_peer_close", "jtb_peer_free",
 ]
 
@@ -56,6 +61,30 @@ def _bind(lib):
     lib.jtb_peer_open.argtypes = [ci, C.c_char_p, C.POINTER(vp)]
     lib.jtb_peer_close.argtypes = [ci, vp]
     lib.jtb_peer_free.argtypes = [ci, vp]
+    lib.jtb_plan_set_devices.argtypes = [vp, ci, C.POINTER(ci)]
+    lib.jtb_plan_device_count.argtypes = [vp]
+    lib.jtb_exec_n.argtypes = [vp, ci, vp, i64, i64, ci]
+    lib.jtb_slab_create.argtypes = [C.POINTER(vp), ci, i64, i64, i64, ci, ci, ci]
+    lib.jtb_slab_destroy.argtypes = [vp]
+    lib.jtb_slab_export.argtypes = [vp, C.c_char_p]
+    lib.jtb_slab_connect_ipc.argtypes = [vp, C.c_char_p]
+    lib.jtb_slab_connect_local.argtypes = [C.POINTER(vp), ci]
+    lib.jtb_nccl_unique_id.argtypes = [C.c_char_p]
+    lib.jtb_slab_nccl_init.argtypes = [vp, C.c_char_p]
+    lib.jtb_slab_nccl_init_local.argtypes = [C.POINTER(vp), ci]
+    lib.jtb_slab_set_exchange.argtypes = [vp, ci]
+    lib.jtb_slab_block_elements.argtypes = [vp]
+    lib.jtb_slab_block_elements.restype = i64
+    lib.jtb_slab_forward.argtypes = [vp, vp, ci, ci, C.POINTER(vp), vp]
+    lib.jtb_slab_back.argtypes = [vp, vp, ci, C.POINTER(vp), vp]
+    lib.jtb_slab_group_forward.argtypes = [C.POINTER(vp), ci, C.POINTER(vp), ci, ci, C.POINTER(vp), C.POINTER(vp)]
+    lib.jtb_slab_group_back.argtypes = [C.POINTER(vp), ci, C.POINTER(vp), ci, C.POINTER(vp), C.POINTER(vp)]
+    lib.jtb_slab_status.argtypes = [vp]
+    lib.jtb_slab_profile.argtypes = [vp, ci]
+    lib.jtb_slab_last_times.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.jtb_lines_c2c_out_device.argtypes = [ci, ci, vp, vp, i64, i64, i64, i64, i64, i64, i64, ci, C.c_double, vp]
+    lib.jtb_debug_table_bytes.argtypes = [ci]
+    lib.jtb_debug_table_bytes.restype = i64
     lib.jtb_debug_set_limits.argtypes = [ci, ci]
     lib.jtb_launch_count.argtypes = [ci]
     lib.jtb_launch_count.restype = i64
@@ -90,4 +119,6 @@ def check(status: int):
         raise ValueError(msg)            # Java shim: IllegalArgumentException(msg)
     if status == ERR_OOM:
         raise MemoryError(msg)
+    if status == ERR_NCCL:
+        raise JtbError("libjtb200 NCCL error: %s" % msg)
     raise JtbError("libjtb200 error %d: %s" % (status, msg))

@@ -16,13 +16,26 @@ class Plan:
     """Owns one jtb_plan*.  Immutable after construction and safe to share between threads (unlike the
     reference's 2-D/3-D objects, fft/DoubleFFT_2D.java:119, fft/DoubleFFT_3D.java:149-162)."""
 
-    def __init__(self, kind: int, prec: int, dims, device: int = 0):
+    def __init__(self, kind: int, prec: int, dims, device: int = 0, devices=None):
+        """``devices``: list of CUDA ordinals for a multi-GPU plan (jtb_plan_set_devices): host-array calls of a
+        3-D FFT plan are slab-decomposed over them, batches are split between them."""
+        if devices is not None and len(devices) > 0:
+            device = int(devices[0])
         self.kind, self.prec, self.dims, self.device = kind, prec, tuple(int(d) for d in dims), device
         self.np_dtype = np.float64 if prec == _lib.F64 else np.float32
         self.total = int(np.prod(self.dims))
         self._h = C.c_void_p()
         arr = (C.c_int64 * len(self.dims))(*self.dims)
         _lib.check(_lib.get().jtb_plan_create(C.byref(self._h), kind, prec, len(self.dims), arr, device))
+        self.devices = [device]
+        if devices is not None and len(devices) > 1:
+            self.set_devices(devices)
+
+    def set_devices(self, devices):
+        devs = [int(d) for d in devices]
+        arr = (C.c_int * len(devs))(*devs)
+        _lib.check(_lib.get().jtb_plan_set_devices(self._h, len(devs), arr))
+        self.devices, self.device = devs, devs[0]
 
     def __del__(self):
         try:
@@ -57,6 +70,10 @@ class Plan:
         if a.size < need:
             # the reference surfaces this as ArrayIndexOutOfBoundsException
             raise IndexError("array of %d elements is too short (need %d)" % (a.size, need))
+        if howmany == 1:
+            # the length travels with the call: the library refuses to touch elements beyond it (jtb_exec_n)
+            _lib.check(_lib.get().jtb_exec_n(self._h, op, C.c_void_p(a.ctypes.data), a.size, offa, int(bool(scale))))
+            return a
         _lib.check(_lib.get().jtb_exec_batch(self._h, op, C.c_void_p(a.ctypes.data), offa, howmany, dist,
                                              int(bool(scale))))
         return a

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libjtb200.so")
-UNITS = ["jtb_ctx", "tile_f64", "tile_f32", "jtb_capi", "jtb_fast", "jtb_fast2", "jtb_mixed", "jtb_r2r_inv", "jtb_stage"]
+UNITS = ["jtb_ctx", "tile_f64", "tile_f32", "jtb_capi", "jtb_fast", "jtb_fast2", "jtb_mixed", "jtb_r2r_inv", "jtb_stage", "jtb_tma", "jtb_slab"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -57,7 +57,7 @@ def build_variant(name: str, defines) -> str:
     os.makedirs(objdir, exist_ok=True)
     with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
         objs = list(ex.map(lambda u: _compile(u, False, objdir, defines), UNITS))
-    r = subprocess.run([NVCC, "-shared", "-o", out] + objs + ["-lcudart"], capture_output=True, text=True)
+    r = subprocess.run([NVCC, "-shared", "-o", out] + objs + ["-lcudart", "-ldl"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stderr)
     return out
@@ -70,7 +70,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     units = [u for u in UNITS if os.path.exists(os.path.join(CSRC, u + ".cu"))]
     with ThreadPoolExecutor(max_workers=len(units)) as ex:
         objs = list(ex.map(lambda u: _compile(u, verbose), units))
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stderr)

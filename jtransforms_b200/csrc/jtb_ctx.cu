@@ -59,6 +59,13 @@ int Ctx::ensure_pipeline() {
   return ST_OK;
 }
 
+void* Ctx::table(const std::string& key) {
+  auto it = tables.find(key);
+  if (it == tables.end()) return nullptr;
+  if (recorder && recorder->insert(key).second) it->second.refs++;
+  return it->second.p;
+}
+
 int Ctx::put_table(const std::string& key, const void* host, size_t bytes, void** dev_out) {
   void* d = nullptr;
   JTB_CUDA(cudaMalloc(&d, bytes < 16 ? 16 : bytes));
@@ -67,9 +74,69 @@ int Ctx::put_table(const std::string& key, const void* host, size_t bytes, void*
   // a pageable H2D cudaMemcpy may return before the DMA has landed; kernels on our non-blocking streams would
   // otherwise be able to read a half-written table
   JTB_CUDA(cudaDeviceSynchronize());
-  tables[key] = d;
   *dev_out = d;
+  return adopt_table(key, d, bytes);
+}
+
+int Ctx::adopt_table(const std::string& key, void* dev, size_t bytes) {
+  TableEntry& t = tables[key];
+  t.p = dev; t.bytes = bytes;
+  if (recorder && recorder->insert(key).second) t.refs++;
   return ST_OK;
+}
+
+// Tables a destroyed plan was the last user of are freed (a caller sweeping over sizes -- the reference's benchmark
+// loop -- would otherwise grow the cache monotonically; a Bluestein plan at n = 10^6 holds ~50 MB).  Small tables
+// (stage twiddles, a few KiB, keyed by log2 n: a bounded set) stay cached.
+void Ctx::release_tables(const std::set<std::string>& keys) {
+  bool synced = false;
+  for (const auto& k : keys) {
+    auto it = tables.find(k);
+    if (it == tables.end()) continue;
+    if (--it->second.refs > 0 || it->second.bytes < ((size_t)64 << 10)) continue;
+    if (!synced) { cudaSetDevice(device); cudaDeviceSynchronize(); synced = true; }   // kernels in flight may read it
+    cudaFree(it->second.p);
+    tables.erase(it);
+    ++table_gen;
+  }
+}
+
+int Ctx::order_begin(cudaStream_t st) {
+  if (has_last && st != last_stream) {
+    if (!ev_order) JTB_CUDA(cudaEventCreateWithFlags(&ev_order, cudaEventDisableTiming));
+    JTB_CUDA(cudaStreamWaitEvent(st, ev_order, 0));
+  }
+  return ST_OK;
+}
+int Ctx::order_end(cudaStream_t st) {
+  if (!ev_order) JTB_CUDA(cudaEventCreateWithFlags(&ev_order, cudaEventDisableTiming));
+  JTB_CUDA(cudaEventRecord(ev_order, st));
+  last_stream = st; has_last = true;
+  return ST_OK;
+}
+
+int Ctx::ensure_watchdog() {
+  if (wd_dev) return ST_OK;
+#ifdef JTB_EMU
+  wd_host = (volatile int*)calloc(1, sizeof(int));
+  wd_dev = (int*)wd_host;
+#else
+  void* h = nullptr;
+  JTB_CUDA(cudaHostAlloc(&h, sizeof(int), cudaHostAllocMapped));
+  *(volatile int*)h = 0;
+  void* d = nullptr;
+  JTB_CUDA(cudaHostGetDevicePointer(&d, h, 0));
+  wd_host = (volatile int*)h; wd_dev = (int*)d;
+#endif
+  return ST_OK;
+}
+int Ctx::check_watchdog(const char* where) {
+  if (!wd_host || *wd_host == 0) return ST_OK;
+  const int code = *wd_host;
+  *wd_host = 0;
+  set_error("%s: a device-side wait timed out on device %d (code %d: %s); the result is invalid", where, device, code,
+            code == 1 ? "slice team barrier" : "peer barrier -- a peer GPU did not publish its epoch");
+  return ST_CUDA;
 }
 
 static std::mutex g_ctx_mu;
@@ -86,7 +153,8 @@ Ctx* get_ctx(int device) {
     return nullptr;
   }
   if (device < 0 || device >= count) { set_error("device %d out of range (have %d)", device, count); return nullptr; }
-  if ((e = cudaSetDevice(device)) != cudaSuccess) { cuda_fail(e, "cudaSetDevice"); return nullptr; }
+  DeviceGuard dg(device);
+  if (!dg.ok) { cuda_fail(cudaGetLastError(), "cudaSetDevice"); return nullptr; }
   Ctx* c = new Ctx();
   c->device = device;
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {

@@ -2,8 +2,10 @@
 // table caches) and the typed transform drivers that turn one JTransforms API call into
 // a short sequence of sm_100a kernel launches.
 #pragma once
+#include <functional>
 #include <map>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -40,6 +42,12 @@ struct DevBuf {
 
 enum { WK_FOURSTEP = 0, WK_BLUE = 1, WK_REAL = 2, WK_FULL = 3, WK_BIG = 4, WK_COUNT = 5 };
 
+struct TableEntry {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int refs = 0;       // plans that looked this table up (jtb_plan_destroy releases them)
+};
+
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;       // library stream for the host-pointer API
@@ -49,20 +57,50 @@ struct Ctx {
   cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined batch path (created on first use)
   cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_c[3] = {nullptr, nullptr, nullptr}, ev_out[3] = {nullptr, nullptr, nullptr};
   int ensure_pipeline();
-  std::map<std::string, void*> tables; // device tables keyed by name
+  std::map<std::string, TableEntry> tables;   // device tables keyed by name
+  std::set<std::string>* recorder = nullptr;  // keys touched by the plan whose call is running (under `mu`)
+  unsigned long table_gen = 0;                // bumped whenever a table is freed (invalidates pointer memos)
   size_t work_cap = (size_t)8 << 30;   // chunk limit per workspace
   long launches = 0;                   // kernels launched (bench.py reports this)
   bool tile_init_done[2] = {false, false};
+  // The workspaces above are shared by every caller stream of this device.  Calls are enqueued under `mu`; when a
+  // call arrives on another stream than the previous one it first waits for the event recorded at the end of that
+  // previous call, so two streams never run library kernels on the same workspace concurrently.
+  cudaEvent_t ev_order = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool has_last = false;
+  int order_begin(cudaStream_t st);
+  int order_end(cudaStream_t st);
+  // watchdog word of the spin-waiting kernels (team barrier of fft_slice2d_kernel, peer_barrier_kernel): mapped
+  // pinned host memory, written by the device on a time-out, read and cleared by the host at the next sync point
+  int* wd_dev = nullptr;
+  volatile int* wd_host = nullptr;
+  int ensure_watchdog();
+  int check_watchdog(const char* where);   // ST_CUDA + message when a kernel gave up waiting
   int ensure(DevBuf& b, size_t bytes);
-  void* table(const std::string& key) { auto it = tables.find(key); return it == tables.end() ? nullptr : it->second; }
+  void* table(const std::string& key);
   int put_table(const std::string& key, const void* host, size_t bytes, void** dev_out);
-  int adopt_table(const std::string& key, void* dev) { tables[key] = dev; return ST_OK; }
+  int adopt_table(const std::string& key, void* dev, size_t bytes = 0);
+  void release_tables(const std::set<std::string>& keys);   // jtb_plan_destroy
+};
+
+// RAII: every entry point makes its device current and restores the caller's on exit
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+    if (prev != device) ok = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
 extern int g_limit_contig, g_limit_strided;   // test knobs: force the two-pass path at small sizes (0 = off)
 Ctx* get_ctx(int device);   // creates on first use; nullptr + error on failure
 bool host_is_pageable(const void* p);                                                                   // jtb_stage.cu
 int staged_copy(int device, void* dev, void* host, size_t bytes, bool to_device, cudaEvent_t after);   // jtb_stage.cu
+int staged_copy_2d(int device, void* dev, void* host, size_t hpitch, size_t width, size_t rows, bool to_device,
+                   cudaEvent_t after, int max_threads);                                                   // jtb_stage.cu
 void grid_for(i64 work_items, unsigned* grid, unsigned* block);
 
 // Fusion options of one power-of-two c2c call (see TileParams)
@@ -109,6 +147,13 @@ template <typename T> struct Engine {
 template <typename T>
 int fast_scatter(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, int nranks, int rank, void* const* peers,
                  bool inverse, i64 slice_base = -1, bool back = false);   // jtb_fast.cu
+template <typename T>
+int fast_c2c_out(Engine<T>& e, cx<T>* a, const Geo& g, cx<T>* out, i64 out_dist, i64 out_stride, i64 nlines, int logn,
+                 bool inverse, bool has_scale, T scale, bool* handled);   // jtb_fast.cu
+template <typename T> bool fast_has_strided(int logn, i64 c0);   // jtb_fast.cu
+template <typename T>
+int fast_tma_c2c(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, int logn, bool inverse, bool has_scale, T scale,
+                 bool* handled);   // jtb_tma.cu
 template <typename T> int fast_stage_table(Engine<T>& e, int logn, int loge, const cx<T>** out);   // jtb_fast.cu
 template <typename T>
 int fast_fourstep_contig(Engine<T>& e, const cx<T>* in, i64 in_dist, cx<T>* out, i64 out_dist, i64 l0, i64 l1, int logn,

@@ -86,8 +86,11 @@ template <typename T> int Engine<T>::tile_tables(int logn, const C** tw, const C
 template <typename T> int Engine<T>::fs_tables(int logN, const C** A, const C** B, int* logL) {
   const int lL = logN / 2;
   // hot-path cache in front of the string-keyed table map
-  static thread_local struct { const void* ctx; int logn; const C* a; const C* b; } memo = {nullptr, 0, nullptr, nullptr};
-  if (memo.ctx == (const void*)ctx && memo.logn == logN) { *A = memo.a; *B = memo.b; *logL = lL; return ST_OK; }
+  static thread_local struct { const void* ctx; int logn; unsigned long gen; const C* a; const C* b; } memo = {nullptr, 0, 0, nullptr, nullptr};
+  if (memo.ctx == (const void*)ctx && memo.logn == logN && memo.gen == ctx->table_gen && !ctx->recorder) {
+    *A = memo.a; *B = memo.b; *logL = lL;
+    return ST_OK;
+  }
   const i64 N = 1LL << logN, L = 1LL << lL, H = N >> lL;
   const std::string ka = mkkey("fsA", pname(), logN), kb = mkkey("fsB", pname(), logN);
   void* da = ctx->table(ka);
@@ -100,7 +103,7 @@ template <typename T> int Engine<T>::fs_tables(int logN, const C** A, const C** 
     JTB_TRY(ctx->put_table(kb, hb.data(), hb.size() * sizeof(C), &db));
   }
   *A = (const C*)da; *B = (const C*)db; *logL = lL;
-  memo.ctx = (const void*)ctx; memo.logn = logN; memo.a = *A; memo.b = *B;
+  memo.ctx = (const void*)ctx; memo.logn = logN; memo.gen = ctx->table_gen; memo.a = *A; memo.b = *B;
   return ST_OK;
 }
 
@@ -141,8 +144,8 @@ template <typename T> int Engine<T>::blue_tables(i64 n, const C** bk1, const C**
       JTB_LAUNCH(k_cast_c64_c32, g, b, 0, st, b2, (float2*)d2, M);
       JTB_CUDA(cudaGetLastError());
       ctx->launches += 2;
-      ctx->adopt_table(k1, d1);
-      ctx->adopt_table(k2, d2);
+      ctx->adopt_table(k1, d1, (size_t)n * sizeof(C));
+      ctx->adopt_table(k2, d2, (size_t)M * sizeof(C));
     }
   }
   *bk1 = (const C*)d1; *bk2 = (const C*)d2;

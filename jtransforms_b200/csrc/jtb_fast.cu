@@ -92,11 +92,23 @@ template <typename T> int fast_stage_table(Engine<T>& e, int logn, int loge, con
 template int fast_stage_table<double>(Engine<double>&, int, int, const double2**);
 template int fast_stage_table<float>(Engine<float>&, int, int, const float2**);
 
+template <typename T>
+int fast_c2c_out(Engine<T>& e, cx<T>* a, const Geo& g, cx<T>* out, i64 out_dist, i64 out_stride, i64 nlines, int logn,
+                 bool inverse, bool has_scale, T scale, bool* handled);
+
 // Runs the lean kernel when the call is a plain in-place transform on a supported layout.
 // *handled = false (and ST_OK) when the caller must use the general tile kernel.
 template <typename T>
 int fast_c2c(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, int logn, bool inverse, bool has_scale, T scale,
              bool* handled) {
+  return fast_c2c_out<T>(e, a, g, nullptr, 0, 0, nlines, logn, inverse, has_scale, scale, handled);
+}
+
+// `out` != null (strided layouts only): the transformed line groups are stored to out + group*out_dist with element
+// stride out_stride instead of in place
+template <typename T>
+int fast_c2c_out(Engine<T>& e, cx<T>* a, const Geo& g, cx<T>* out, i64 out_dist, i64 out_stride, i64 nlines, int logn,
+                 bool inverse, bool has_scale, T scale, bool* handled) {
   *handled = false;
   static const bool off = getenv("JTB_NO_FAST") != nullptr;
   if (off || nlines <= 0) return ST_OK;
@@ -107,6 +119,11 @@ int fast_c2c(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, int logn, bool in
   else if (g.stride > 1 && g.d[0] == 1 && g.c[1] == 1 && g.c[2] == 1 && g.c[0] > 1 &&
            (n - 1) * g.stride + g.c[0] < 0x7fffffffLL && nlines % g.c[0] == 0) strided = true;
   else return ST_OK;
+  if (out && (!strided || out_stride >= 0x7fffffffLL)) return ST_OK;
+  if (strided && !out) {   // persistent TMA-fed kernel (jtb_tma.cuh) where a variant exists
+    JTB_TRY(fast_tma_c2c<T>(e, a, g, nlines, logn, inverse, has_scale, scale, handled));
+    if (*handled) return ST_OK;
+  }
   const char* ev = getenv(strided ? "JTB_FAST_WS" : "JTB_FAST_WC");
   const int wwant = ev ? atoi(ev) : 0;
   FastEntry<T>* pick = nullptr;
@@ -127,16 +144,23 @@ int fast_c2c(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, int logn, bool in
   p.line_dist = g.d[3]; p.c0 = (int)g.c[0]; p.stride = (int)g.stride;
   p.inverse = inverse; p.has_scale = has_scale; p.scale = scale;
   JTB_TRY(fast_stage_table<T>(e, pick->logn, pick->loge, &p.twg));
+  p.out = out ? out : a; p.out_line_dist = out ? out_dist : g.d[3]; p.out_stride = out ? (int)out_stride : (int)g.stride;
   p.reps = 1;
+  p.prefetch = 0;
   if (strided) {
     // lines whose elements are >= 2 MB apart touch one TLB page per element: let a CTA reuse its translations for a
     // few neighbouring column groups (JTB_FAST_REPS overrides)
     const char* er = getenv("JTB_FAST_REPS");
     const i64 bytes_stride = g.stride * (i64)sizeof(cx<T>);
     p.reps = er ? atoi(er) : 1;   // measured: no gain from 2..8 on the 4 MiB-stride pass
-    (void)bytes_stride;
     if (p.reps < 1) p.reps = 1;
     while (p.reps > 1 && ((g.c[0] / pick->W) % p.reps) != 0) --p.reps;
+    // L2 prefetch of the tile this many CTAs ahead.  Measured on B200, 512^3 double: row-stride (8 KiB) column pass
+    // 0.694 -> 0.660 ms at 74..111 (0.645 at 148); slice-stride (4 MiB) pass 0.80 -> 1.10 ms (every prefetched row
+    // is its own page) -> on for strides up to 64 KiB only.  JTB_FAST_PREFETCH overrides (0 = off).
+    static const char* epf = getenv("JTB_FAST_PREFETCH");
+    const int pf_default = (sizeof(T) == 8 && bytes_stride <= (64 << 10)) ? 111 : 0;
+    p.prefetch = p.reps == 1 ? (epf ? atoi(epf) : pf_default) : 0;
   }
   const i64 nblk = ((nlines + pick->W - 1) / pick->W + p.reps - 1) / p.reps;
   if (nblk > 0x7fffffffLL) return ST_OK;
@@ -266,7 +290,8 @@ int fast_slice2d(Engine<T>& e, cx<T>* a, i64 nslices, i64 N, bool inverse, bool 
   Slice2DParams<T> p;
   memset(&p, 0, sizeof p);
   p.a = a; p.nslices = (int)nslices; p.team = team;
-  p.counters = sc[dv].p + 1; p.err = sc[dv].p;
+  JTB_TRY(e.ctx->ensure_watchdog());
+  p.counters = sc[dv].p + 1; p.err = e.ctx->wd_dev;   // time-outs are read back by Ctx::check_watchdog
   JTB_TRY(fast_stage_table<T>(e, 9, 3, &p.twg));
   p.inverse = inverse; p.has_scale = has_scale; p.scale = scale;
   {
@@ -291,12 +316,8 @@ int peer_barrier(Ctx* ctx, cudaStream_t st, void* const* flag_ptrs, int nranks, 
   if (nranks < 1 || nranks > 8) { set_error("1..8 ranks"); return ST_ARG; }
   PeerFlags pf;
   for (int h = 0; h < 8; ++h) pf.f[h] = h < nranks ? (long long*)flag_ptrs[h] : nullptr;
-  static int* err = nullptr;
-  if (!err) {
-    JTB_CUDA(cudaMalloc((void**)&err, sizeof(int)));
-    JTB_CUDA(cudaMemset(err, 0, sizeof(int)));
-  }
-  JTB_LAUNCH(peer_barrier_kernel, 1u, 32u, 0, st, pf, nranks, rank, epoch, err);
+  JTB_TRY(ctx->ensure_watchdog());   // per-device flag; a time-out surfaces through Ctx::check_watchdog
+  JTB_LAUNCH(peer_barrier_kernel, 1u, 32u, 0, st, pf, nranks, rank, epoch, ctx->wd_dev);
   JTB_CUDA(cudaGetLastError());
   ctx->launches++;
   return ST_OK;
@@ -304,7 +325,18 @@ int peer_barrier(Ctx* ctx, cudaStream_t st, void* const* flag_ptrs, int nranks, 
 
 template int fast_scatter<double>(Engine<double>&, const double2*, i64, i64, i64, int, int, void* const*, bool, i64, bool);
 template int fast_scatter<float>(Engine<float>&, const float2*, i64, i64, i64, int, int, void* const*, bool, i64, bool);
+// true when a lean strided kernel exists for 2^logn-point lines in groups of c0 adjacent lines
+template <typename T> bool fast_has_strided(int logn, i64 c0) {
+  for (auto& f : registry<T>())
+    if (f.logn == logn && f.strided && c0 % f.W == 0) return true;
+  return false;
+}
+template bool fast_has_strided<double>(int, i64);
+template bool fast_has_strided<float>(int, i64);
+
 template int fast_c2c<double>(Engine<double>&, double2*, const Geo&, i64, int, bool, bool, double, bool*);
 template int fast_c2c<float>(Engine<float>&, float2*, const Geo&, i64, int, bool, bool, float, bool*);
+template int fast_c2c_out<double>(Engine<double>&, double2*, const Geo&, double2*, i64, i64, i64, int, bool, bool, double, bool*);
+template int fast_c2c_out<float>(Engine<float>&, float2*, const Geo&, float2*, i64, i64, i64, int, bool, bool, float, bool*);
 
 }  // namespace jtb

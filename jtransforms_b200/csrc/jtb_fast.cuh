@@ -29,6 +29,12 @@ template <typename T> struct FastParams {
   T scale;
   const cx<T>* twg;  // base twiddles, layout below (fast_twiddle_count entries)
   int reps;          // strided layout: consecutive groups of W lines handled by one CTA (TLB / launch amortisation)
+  int prefetch;      // strided layout: prefetch.global.L2 of the tile `prefetch` CTAs ahead (0 = off)
+  // strided layout, out of place: the same line groups stored with another group distance / element stride (the
+  // axis-swapping k2 pass of the 3-D transform).  out == a, same distances: in place.
+  cx<T>* out;
+  i64 out_line_dist;
+  int out_stride;
 };
 
 // four consecutive reals with one request: 256-bit LDG/STG for double (sm_100a: ld.global.v4.f64, 32-byte aligned),
@@ -157,17 +163,34 @@ template <typename T, typename S, int s, bool STRIDED, int W> struct FastStage {
   }
 };
 
-template <typename T, typename S, int s, bool STRIDED, int W> struct FastLoop {
+// Barrier used between the stages: the whole CTA (default), or a named barrier over one compute group of a
+// warp-specialised persistent kernel (jtb_tma.cuh), where several groups work on different tiles of one CTA.
+struct SyncCta {
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+template <int THREADS> struct SyncGroup {
+  int id;   // named barrier 1..15
+  __device__ __forceinline__ void sync() const {
+#ifdef JTB_EMU
+    __syncthreads();
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(THREADS) : "memory");
+#endif
+  }
+};
+
+template <typename T, typename S, int s, bool STRIDED, int W, typename SY = SyncCta> struct FastLoop {
   typedef FastAddr<T, S, STRIDED, W> A;
-  __device__ static __forceinline__ void run(cx<T>* v, cx<T>* sm, const cx<T>* twt, int t, int w, const cx<T>* twg) {
+  __device__ static __forceinline__ void run(cx<T>* v, cx<T>* sm, const cx<T>* twt, int t, int w, const cx<T>* twg,
+                                             const SY sy = SY()) {
     FastStage<T, S, s, STRIDED, W>::compute(v, t, twt, twg);
     if (s + 1 < S::S) {
-      if (s > 0) __syncthreads();
+      if (s > 0) sy.sync();
       FastStage<T, S, s, STRIDED, W>::scatter(v, sm, t, w);
-      __syncthreads();
+      sy.sync();
 #pragma unroll
       for (int q = 0; q < S::E; ++q) v[q] = sm[A::at(t + q * S::TPL, w)];
-      FastLoop<T, S, (s + 1 < S::S ? s + 1 : s), STRIDED, W>::run(v, sm, twt, t, w, twg);
+      FastLoop<T, S, (s + 1 < S::S ? s + 1 : s), STRIDED, W, SY>::run(v, sm, twt, t, w, twg, sy);
     }
   }
 };
@@ -191,21 +214,36 @@ fft_fast_kernel(const FastParams<T> p) {
   if (STRIDED) { w = tid % W; t = tid / W; } else { t = tid % S::TPL; w = tid / S::TPL; }
   for (int i = tid; i < FastTw<S>::COUNT_SM; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
 
+#ifndef JTB_EMU
+  if (STRIDED && p.prefetch > 0) {
+    // pull the rows of a later tile into L2 while this one is transformed (one 128-byte row segment per thread)
+    const i64 pl0 = ((i64)blockIdx.x + p.prefetch) * W;
+    if (pl0 < p.nlines) {
+      const i64 grp = pl0 / p.c0;
+      const C* pb = p.a + grp * p.line_dist + (pl0 - grp * p.c0);
+      for (int i = tid; i < S::N; i += W * S::TPL) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + (i64)i * p.stride));
+    }
+  }
+#endif
   for (int rep = 0; rep < (STRIDED ? p.reps : 1); ++rep) {
     const i64 line0 = ((i64)blockIdx.x * (STRIDED ? p.reps : 1) + rep) * W;
     if (line0 >= p.nlines) break;
     C* base;
-    int es;
+    C* obase;
+    int es, oes;
     bool valid = true;
     if (STRIDED) {
       const i64 grp = line0 / p.c0;
       const int c = (int)(line0 - grp * p.c0);
       base = p.a + grp * p.line_dist + c + w;
       es = p.stride;
+      obase = p.out + grp * p.out_line_dist + c + w;
+      oes = p.out_stride;
     } else {
       valid = line0 + w < p.nlines;
       base = p.a + (valid ? (line0 + w) * p.line_dist : 0);
       es = 1;
+      obase = base; oes = 1;
     }
     C v[S::E];
     if (valid) {
@@ -231,7 +269,7 @@ fft_fast_kernel(const FastParams<T> p) {
     }
     if (valid) {
 #pragma unroll
-      for (int q = 0; q < S::E; ++q) base[(t + q * S::TPL) * es] = v[q];
+      for (int q = 0; q < S::E; ++q) obase[(i64)(t + q * S::TPL) * oes] = v[q];
     }
   }
 }
@@ -433,7 +471,7 @@ static __global__ void peer_barrier_kernel(const PeerFlags flags, int nranks, in
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   while (*mine < epoch) {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    if (t1 - t0 > 10000000000ULL) { *err = 1; break; }   // 10 s: a peer died; give up instead of hanging the GPU
+    if (t1 - t0 > 10000000000ULL) { *err = 2; break; }   // 10 s: a peer died; give up instead of hanging the GPU
   }
   __threadfence_system();
 #endif

@@ -617,7 +617,7 @@ int fast_bluestein_contig(Engine<T>& e, cx<T>* a, i64 dist, i64 nlines, i64 n, b
     JTB_LAUNCH(k_permute_bk2<C>, gr, bl, 0, e.st, bk2, bk2p, fa->logn, fb->logn);
     JTB_CUDA(cudaGetLastError());
     e.ctx->launches++;
-    e.ctx->adopt_table(kp, bk2p);
+    e.ctx->adopt_table(kp, bk2p, (size_t)M * sizeof(C));
   }
   const C *fsA, *fsB;
   int logL;

@@ -33,8 +33,13 @@ def _args(args, want_scale: bool):
 class _FFT:
     _prec = _lib.F64
 
-    def __init__(self, *dims, device: int = 0):
-        self._plan = Plan(_lib.FFT, self._prec, dims, device)
+    def __init__(self, *dims, device: int = 0, devices=None):
+        self._plan = Plan(_lib.FFT, self._prec, dims, device, devices)
+
+    def setDevices(self, devices):
+        """Multi-GPU: spread host-array transforms (3-D: slab decomposition; batches: blocks) over these GPUs --
+        the role ConcurrencyUtils.setNumberOfThreads plays for the reference's thread pool."""
+        self._plan.set_devices(devices)
 
     # fft/DoubleFFT_1D.java:243-263, fft/DoubleFFT_2D.java:115-213, fft/DoubleFFT_3D.java:145-325
     def complexForward(self, a, *args):
@@ -68,8 +73,8 @@ class _FFT:
 
 
 class DoubleFFT_1D(_FFT):
-    def __init__(self, n, device: int = 0):
-        super().__init__(n, device=device)
+    def __init__(self, n, device: int = 0, devices=None):
+        super().__init__(n, device=device, devices=devices)
 
     # extension used by config 3 (the reference loops over offa, fft/FloatFFT_1D.java:243)
     def complexForwardBatch(self, a, howmany: int, dist: int, offa: int = 0):
@@ -77,13 +82,13 @@ class DoubleFFT_1D(_FFT):
 
 
 class DoubleFFT_2D(_FFT):
-    def __init__(self, rows, columns, device: int = 0):
-        super().__init__(rows, columns, device=device)
+    def __init__(self, rows, columns, device: int = 0, devices=None):
+        super().__init__(rows, columns, device=device, devices=devices)
 
 
 class DoubleFFT_3D(_FFT):
-    def __init__(self, slices, rows, columns, device: int = 0):
-        super().__init__(slices, rows, columns, device=device)
+    def __init__(self, slices, rows, columns, device: int = 0, devices=None):
+        super().__init__(slices, rows, columns, device=device, devices=devices)
 
 
 class FloatFFT_1D(DoubleFFT_1D):

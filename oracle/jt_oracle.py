@@ -35,6 +35,13 @@ from __future__ import annotations
 import numpy as np
 import scipy.fft as sfft
 
+
+def _workers(x) -> int:
+    """Host threads for the big configurations (512^3, 8192^2): same pocketfft arithmetic, just not on one core."""
+    import os
+    return (os.cpu_count() or 1) if np.size(x) >= (1 << 22) else 1
+
+
 # --------------------------------------------------------------------------
 # helpers
 # --------------------------------------------------------------------------
@@ -454,7 +461,7 @@ def complex_forward_3d(a, slices, rows, cols):
     """DoubleFFT_3D.complexForward (fft/DoubleFFT_3D.java:145-325);
     a[k1*sliceStride + k2*rowStride + 2*k3] (doc :127-141)."""
     z = i2c(np.asarray(a, dtype=np.float64).reshape(slices, rows, 2 * cols))
-    return c2i(np.fft.fftn(z)).ravel()
+    return c2i(sfft.fftn(z, workers=_workers(z))).ravel()
 
 
 def complex_inverse_3d(a, slices, rows, cols, scale):
@@ -632,8 +639,8 @@ def dct_forward_1d(x, scale: bool):
     if n == 1:
         return x.copy()
     if scale:
-        return sfft.dct(x, type=2, norm="ortho", axis=-1)
-    y = sfft.dct(x, type=2, axis=-1)  # scipy: 2*sum
+        return sfft.dct(x, type=2, norm="ortho", axis=-1, workers=_workers(x))
+    y = sfft.dct(x, type=2, axis=-1, workers=_workers(x))  # scipy: 2*sum
     return y * 0.5 if is_pow2(n) else y
 
 
@@ -738,7 +745,7 @@ def dht_forward_nd(a, shape):
     H = Re(F) - Im(F) with F = fftn(x) (checked in tests/test_oracle.py against a
     literal restatement of yTransform, ``sim_dht_nd``)."""
     x = np.asarray(a, dtype=np.float64).reshape(shape)
-    F = np.fft.fftn(x)
+    F = sfft.fftn(x, workers=_workers(x))
     return (F.real - F.imag).ravel()
 
 

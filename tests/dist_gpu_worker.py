@@ -14,7 +14,8 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 for mode in ("p2p", "nccl"):
-    for (S, R, Cn) in [(64, 64, 64), (16, 512, 32), (8 * world, 64, 24), (2 * world, 512, 512)]:
+    for (S, R, Cn) in [(64, 64, 64), (16, 512, 32), (8 * world, 64, 24), (2 * world, 512, 512), (128, 128, 128),
+                       (256, 256, 32), (6 * world, 5 * world, 10)]:
         x = o.fill_uniform(2 * S * R * Cn, seed=11)
         want = o.complex_forward_3d(x, S, R, Cn).reshape(S, R, 2 * Cn)
         f = SlabFFT3D(S, R, Cn, device_index=local, exchange=mode)
@@ -26,6 +27,7 @@ for mode in ("p2p", "nccl"):
             got = res.cpu().numpy().reshape(S, Rh, 2 * Cn)
             err = o.rel_l2(got, want[:, rank * Rh:(rank + 1) * Rh])
             assert err < 1e-12 * 20, (mode, S, R, Cn, it, err)
+            f.status()           # no device-side wait timed out
             if it == 0:          # distributed round trip (inverse of the k2-slabbed spectrum)
                 back = f.inverse(res.clone(), True)
                 torch.cuda.synchronize()

@@ -179,6 +179,24 @@ def r2r(jt, prec, kind, dims):
     check(a, x64, prec, total, "%s round trip %s" % (kind, dims))
 
 
+# ------------------------------------------------------------------ multi-GPU plans through the host API
+def fft3d_multi(jt, prec, dims, devices):
+    """DoubleFFT_3D(..., devices=[...]): one host array in, natural order out (jtb_plan_set_devices + jtb_exec)"""
+    S, R, Cn = dims
+    total = S * R * Cn
+    dt = dtype_of(prec)
+    f = getattr(jt, prec + "FFT_3D")(S, R, Cn, devices=devices)
+    x64 = rnd(2 * total)
+    a = x64.astype(dt)
+    f.complexForward(a)
+    check(a, o.complex_forward_3d(x64, S, R, Cn), prec, total, "multi-GPU forward %s P=%d" % (dims, len(devices)))
+    f.complexInverse(a, True)
+    check(a, x64, prec, total, "multi-GPU round trip %s P=%d" % (dims, len(devices)))
+    b = x64.astype(dt)
+    f.complexInverse(b, False)
+    check(b, o.complex_inverse_3d(x64, S, R, Cn, False), prec, total, "multi-GPU unscaled inverse %s" % (dims,))
+
+
 # ------------------------------------------------------------------ fused k2 + exchange (virtual ranks)
 def slab_scatter_virtual(lib, prec, dims, P, torch_device="cpu", dev_index=0, fused_slices=False):
     """Runs the slab-decomposed forward transform with P *virtual* ranks inside one process: every rank's

@@ -363,3 +363,87 @@ def test_slices_entry_point_virtual_ranks(jt):
     """jtb_fft2d_slices_device with receive buffers (general path in the emulated build)"""
     from jtransforms_b200 import _lib
     pc.slab_scatter_virtual(_lib.get(), "Double", (4, 64, 64), 2, fused_slices=True)
+
+
+# ------------------------------------------------------------------ multi-GPU plans (virtual ranks on the emulated device)
+@pytest.mark.parametrize("prec", ["Double", "Float"])
+@pytest.mark.parametrize("P,dims", [(2, (8, 8, 16)), (4, (8, 8, 16)), (2, (6, 10, 5)), (8, (64, 64, 16)), (4, (4, 64, 64)),
+                                    (3, (6, 9, 4))])
+def test_multi_device_plan_virtual(jt, prec, P, dims):
+    """jtb_plan_set_devices: ONE host array in, natural order out, slab-decomposed over P members (same device listed
+    P times); forward against the oracle, then complexInverse(scale) back to the input"""
+    pc.fft3d_multi(jt, prec, dims, [0] * P)
+
+
+def test_multi_device_plan_pageable(jt, monkeypatch):
+    """pageable caller memory: the per-member staged (pitched) copies deliver the natural order too"""
+    monkeypatch.setenv("JTB_EMU_PAGEABLE", "1")
+    monkeypatch.setenv("JTB_STAGE_MIN_MB", "0")
+    pc.fft3d_multi(jt, "Double", (8, 8, 16), [0, 0])
+    pc.fft3d_multi(jt, "Double", (6, 10, 5), [0, 0])
+
+
+def test_multi_device_batch(jt):
+    """batches on a multi-GPU plan are split into one contiguous block per member"""
+    n, howmany = 100, 7
+    x = pc.rnd(2 * n * howmany)
+    a = x.copy()
+    jt.DoubleFFT_1D(n, devices=[0, 0, 0]).complexForwardBatch(a, howmany, 2 * n)
+    for b in range(howmany):
+        pc.check(a[2 * n * b:2 * n * (b + 1)], o.complex_forward_1d(x[2 * n * b:2 * n * (b + 1)], n), "Double", n, "batch %d" % b)
+    # other ops of a multi-GPU plan run on devices[0]
+    y = pc.rnd(8 * 8 * 16)
+    b2 = y.copy()
+    jt.DoubleFFT_3D(8, 8, 16, devices=[0, 0]).realForward(b2)
+    pc.check(b2, o.real_forward_3d(y, 8, 8, 16), "Double", 1024, "realForward on a multi plan")
+
+
+def test_multi_device_errors(jt):
+    from jtransforms_b200 import _lib
+    with pytest.raises(Exception):
+        jt.DoubleFFT_3D(8, 8, 16, devices=[0, 7])          # no such device
+    f = jt.DoubleFFT_3D(6, 8, 16, devices=[0, 0, 0, 0])      # 6 slices do not divide by 4: no slab path, devices[0] runs it
+    x = pc.rnd(2 * 6 * 8 * 16)
+    a = x.copy()
+    f.complexForward(a)
+    pc.check(a, o.complex_forward_3d(x, 6, 8, 16), "Double", 768, "non-divisible falls back to one device")
+    assert _lib.get().jtb_plan_device_count(f._plan._h) == 4
+
+
+def test_exec_n_bounds(jt):
+    """the C entry point refuses arrays shorter than offa + elements (the Java shim's ArrayIndexOutOfBounds)"""
+    import ctypes as C
+    from jtransforms_b200 import _lib
+    lib = _lib.get()
+    f = jt.DoubleFFT_1D(64)
+    a = np.zeros(128)
+    assert lib.jtb_exec_n(f._plan._h, _lib.C2C_FORWARD, C.c_void_p(a.ctypes.data), 127, 0, 0) == _lib.ERR_ARG
+    assert b"too short" in lib.jtb_last_error()
+    assert lib.jtb_exec_n(f._plan._h, _lib.C2C_FORWARD, C.c_void_p(a.ctypes.data), 128, 1, 0) == _lib.ERR_ARG
+    assert lib.jtb_exec_n(f._plan._h, _lib.C2C_FORWARD, C.c_void_p(a.ctypes.data), 128, 0, 0) == _lib.OK
+
+
+def test_plan_destroy_releases_tables(jt):
+    """a caller sweeping over sizes must not grow the table cache: the chirp tables of a Bluestein plan go with it"""
+    from jtransforms_b200 import _lib
+    lib = _lib.get()
+    base = lib.jtb_debug_table_bytes(0)
+    for n in (10007, 10009, 10037):
+        f = jt.DoubleFFT_1D(n)
+        a = pc.rnd(2 * n)
+        f.complexForward(a)
+        during = lib.jtb_debug_table_bytes(0)
+        assert during > base + 16 * n
+        del f
+        import gc
+        gc.collect()
+        assert lib.jtb_debug_table_bytes(0) < base + 64 * 1024 * 8, "tables of a destroyed plan were not released"
+    # a table shared by two plans survives the first destroy and still gives right answers
+    f1, f2 = jt.DoubleFFT_1D(10007), jt.DoubleFFT_1D(10007)
+    x = pc.rnd(2 * 10007)
+    a1 = x.copy(); f1.complexForward(a1)
+    a2 = x.copy(); f2.complexForward(a2)
+    del f1
+    gc.collect()
+    a3 = x.copy(); f2.complexForward(a3)
+    assert np.array_equal(a2, a3)

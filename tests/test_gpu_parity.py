@@ -286,6 +286,40 @@ def test_dct2d_8192(jt):
     pc.check(a, want, "Double", n * n, "DCT 8192^2")
 
 
+@pytest.mark.parametrize("kind", ["DST", "DHT"])
+def test_dst_dht_2d_8192(jt, kind):
+    """config 4 names all three transforms: DoubleDST_2D / DoubleDHT_2D forward at 8192 x 8192 against the oracle
+    (dst/DoubleDST_2D.java:103, dht/DoubleDHT_2D.java:102-190 + yTransform :1288-1309), element for element"""
+    n = 8192
+    x = o.fill_uniform(n * n, seed=3, lo=-1.0, hi=1.0)
+    a = x.copy()
+    if kind == "DST":
+        jt.DoubleDST_2D(n, n).forward(a, True)
+        want = o.dst_forward_nd(x, (n, n), True)
+    else:
+        jt.DoubleDHT_2D(n, n).forward(a)
+        want = o.dht_forward_nd(x, (n, n))
+    pc.check(a, want, "Double", n * n, "%s 8192^2" % kind)
+
+
+def test_fft3d_512_vs_oracle(jt):
+    """config 5 itself, element for element: the host-array path (jtb_exec) at 512^3 against
+    oracle.complex_forward_3d, tolerance 1e-12 * log2(N) = 27e-12 relative L2 -- and the same array through the
+    8-way slab decomposition (single-process multi-GPU plan, eight virtual ranks on this GPU: the shapes, kernels and
+    exchange addressing of the 8-GPU run)"""
+    S = R = C = 512
+    x = o.fill_uniform(2 * S * R * C, seed=2)
+    want = o.complex_forward_3d(x, S, R, C)
+    a = x.copy()
+    jt.DoubleFFT_3D(S, R, C).complexForward(a)
+    err = o.rel_l2(a, want)
+    assert err <= 27e-12, err
+    a[:] = x
+    jt.DoubleFFT_3D(S, R, C, devices=[0] * 8).complexForward(a)
+    err8 = o.rel_l2(a, want)
+    assert err8 <= 27e-12, err8
+
+
 def test_large_64bit_indexing(jt):
     """arrays beyond 2^31 bytes / 2^30 elements, device resident: 1024^3 complex double (16 GiB) round trip +
     Parseval, and a 2^26-point 1-D transform against the oracle"""
