@@ -154,6 +154,10 @@ int jtb_slab_status(jtb_slab* m);
 /* phase timing of the last step (bench): ms3 = {in-slice passes + exchange stores, wait for peers, slice-axis pass} */
 int jtb_slab_profile(jtb_slab* m, int enable);
 int jtb_slab_last_times(jtb_slab* m, float* ms3);
+/* timeline of the last profiled pipelined step (ms since its start, up to 16 column blocks): stored[j] = block j has left
+ * on the producer stream, done[j] = slice-axis pass of block j finished on the consumer stream; *nblocks = 0 when the
+ * step was not pipelined */
+int jtb_slab_chunk_times(jtb_slab* m, int* nblocks, float* stored, float* done);
 
 /* device-side barrier between the ranks on `stream`: publishes `epoch` into every peer's flag array and waits
  * for all peers to publish it (flag_ptrs[h] = peer-mapped int64[nranks] of rank h, zero-initialised). */

@@ -25,7 +25,7 @@ SYMBOLS = [
     "jtb_slab_create", "jtb_slab_destroy", "jtb_slab_export", "jtb_slab_connect_ipc", "jtb_slab_connect_local",
     "jtb_nccl_unique_id", "jtb_slab_nccl_init", "jtb_slab_nccl_init_local", "jtb_slab_set_exchange",
     "jtb_slab_block_elements", "jtb_slab_forward", "jtb_slab_back", "jtb_slab_group_forward", "jtb_slab_group_back",
-    "jtb_slab_status", "jtb_slab_profile", "jtb_slab_last_times", "jtb_lines_c2c_out_device",
+    "jtb_slab_status", "jtb_slab_profile", "jtb_slab_last_times", "jtb_slab_chunk_times", "jtb_lines_c2c_out_device",
     "jtb_fft3d_k2_scatter", "jtb_fft3d_k2_scatter_chunk", "jtb_fft3d_k1_scatter", "jtb_fft2d_slices_device", "jtb_peer_barrier", "jtb_peer_alloc", "jtb_peer_open", "jtb_peer_close", "jtb_peer_free",
 ]
 
@@ -82,6 +82,7 @@ def _bind(lib):
     lib.jtb_slab_status.argtypes = [vp]
     lib.jtb_slab_profile.argtypes = [vp, ci]
     lib.jtb_slab_last_times.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.jtb_slab_chunk_times.argtypes = [vp, C.POINTER(ci), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.jtb_lines_c2c_out_device.argtypes = [ci, ci, vp, vp, i64, i64, i64, i64, i64, i64, i64, ci, C.c_double, vp]
     lib.jtb_debug_table_bytes.argtypes = [ci]
     lib.jtb_debug_table_bytes.restype = i64

@@ -101,7 +101,22 @@ void Ctx::release_tables(const std::set<std::string>& keys) {
   }
 }
 
+// A stream that is being captured into a CUDA graph takes no part in the cross-stream ordering: an event recorded
+// inside a capture belongs to the graph and can never be waited on from outside it (the caller replays the graph on
+// one stream and owns the ordering of its replays).
+static bool stream_capturing(cudaStream_t st) {
+#ifdef JTB_EMU
+  (void)st;
+  return false;
+#else
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+  return cs != cudaStreamCaptureStatusNone;
+#endif
+}
+
 int Ctx::order_begin(cudaStream_t st) {
+  if (stream_capturing(st)) return ST_OK;
   if (has_last && st != last_stream) {
     if (!ev_order) JTB_CUDA(cudaEventCreateWithFlags(&ev_order, cudaEventDisableTiming));
     JTB_CUDA(cudaStreamWaitEvent(st, ev_order, 0));
@@ -109,6 +124,7 @@ int Ctx::order_begin(cudaStream_t st) {
   return ST_OK;
 }
 int Ctx::order_end(cudaStream_t st) {
+  if (stream_capturing(st)) return ST_OK;
   if (!ev_order) JTB_CUDA(cudaEventCreateWithFlags(&ev_order, cudaEventDisableTiming));
   JTB_CUDA(cudaEventRecord(ev_order, st));
   last_stream = st; has_last = true;

@@ -146,7 +146,8 @@ template <typename T> struct Engine {
 
 template <typename T>
 int fast_scatter(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, int nranks, int rank, void* const* peers,
-                 bool inverse, i64 slice_base = -1, bool back = false);   // jtb_fast.cu
+                 bool inverse, i64 slice_base = -1, bool back = false, i64 col0 = 0, i64 ncols = -1);   // jtb_fast.cu
+template <typename T> int fast_scatter_width(i64 R, i64 Cn);   // jtb_fast.cu
 template <typename T>
 int fast_c2c_out(Engine<T>& e, cx<T>* a, const Geo& g, cx<T>* out, i64 out_dist, i64 out_stride, i64 nlines, int logn,
                  bool inverse, bool has_scale, T scale, bool* handled);   // jtb_fast.cu
@@ -187,7 +188,8 @@ int fast_slice2d(Engine<T>& e, cx<T>* a, i64 nslices, i64 N, bool inverse, bool 
 template <typename T>
 int mixed_c2c(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, i64 n, bool inverse, bool has_scale, T scale,
               bool* handled);   // jtb_mixed.cu
-int peer_barrier(Ctx* ctx, cudaStream_t st, void* const* flag_ptrs, int nranks, int rank, long long epoch);
+// what: 1 publish `epoch` to every peer, 2 wait until every peer has published it, 3 both (barrier)
+int peer_barrier(Ctx* ctx, cudaStream_t st, void* const* flag_ptrs, int nranks, int rank, long long epoch, int what = 3);
 
 extern template struct Engine<double>;
 extern template struct Engine<float>;

@@ -192,18 +192,21 @@ template <typename T, int LOGN, int LOGE, int W> ScatterEntry<T> make_scatter() 
 template <typename T> std::vector<ScatterEntry<T>>& scatter_registry();
 template <> std::vector<ScatterEntry<double>>& scatter_registry<double>() {
   static std::vector<ScatterEntry<double>> r = {make_scatter<double, 9, 3, 8>(), make_scatter<double, 9, 3, 16>(),
-                                                make_scatter<double, 6, 3, 8>(), make_scatter<double, 10, 4, 8>()};
+                                                make_scatter<double, 6, 3, 8>(), make_scatter<double, 10, 4, 8>(),
+                                                make_scatter<double, 7, 4, 16>(), make_scatter<double, 8, 4, 8>()};
   return r;
 }
 template <> std::vector<ScatterEntry<float>>& scatter_registry<float>() {
-  static std::vector<ScatterEntry<float>> r = {make_scatter<float, 9, 3, 16>(), make_scatter<float, 6, 3, 16>()};
+  static std::vector<ScatterEntry<float>> r = {make_scatter<float, 9, 3, 16>(), make_scatter<float, 6, 3, 16>(),
+                                               make_scatter<float, 7, 4, 16>(), make_scatter<float, 8, 4, 16>(),
+                                               make_scatter<float, 10, 4, 16>(), make_scatter<float, 11, 4, 8>()};
   return r;
 }
 }  // namespace
 
 template <typename T>
 int fast_scatter(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, int nranks, int rank, void* const* peers,
-                 bool inverse, i64 slice_base, bool back) {
+                 bool inverse, i64 slice_base, bool back, i64 col0, i64 ncols) {
   if (!is_pow2(R) || nranks < 1 || nranks > 8 || !is_pow2(nranks) || R % nranks) {
     set_error("fused exchange needs power-of-two rows and 1, 2, 4 or 8 ranks");
     return ST_UNSUPPORTED;
@@ -216,6 +219,9 @@ int fast_scatter(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, int nranks
     if (f.logn == logn && Cn % f.W == 0 && (wwant <= 0 || f.W == wwant)) { pick = &f; break; }
   if (!pick) { set_error("no fused-exchange kernel for %lld rows x %lld columns", (long long)R, (long long)Cn); return ST_UNSUPPORTED; }
   if (Ls * (Cn / pick->W) > 0x7fffffffLL || Ls * R * Cn >= (1LL << 40)) { set_error("slab too large"); return ST_UNSUPPORTED; }
+  if (ncols < 0) { col0 = 0; ncols = Cn; }
+  if (col0 < 0 || col0 % pick->W || ncols % pick->W || col0 + ncols > Cn) { set_error("bad column window"); return ST_UNSUPPORTED; }
+  if (ncols == 0) return ST_OK;
   if (!(pick->attr_done & (1u << (e.ctx->device & 31)))) {
     JTB_CUDA(cudaFuncSetAttribute(pick->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pick->smem));
     pick->attr_done |= 1u << (e.ctx->device & 31);
@@ -231,7 +237,8 @@ int fast_scatter(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, int nranks
     p.row_base = (long long)p.slice0 * (R / nranks); p.row_ls_mul = (int)(R / nranks); p.row_mul = 1;
   }
   JTB_TRY(fast_stage_table<T>(e, logn, pick->loge, &p.twg));
-  const unsigned nblk = (unsigned)(Ls * (Cn / pick->W));
+  p.col0 = (int)col0; p.groups = (int)(ncols / pick->W);
+  const unsigned nblk = (unsigned)(Ls * (ncols / pick->W));
   JTB_LAUNCH(pick->kern, nblk, (unsigned)pick->threads, (size_t)pick->smem, e.st, p);
   JTB_CUDA(cudaGetLastError());
   e.ctx->launches++;
@@ -312,19 +319,30 @@ int fast_slice2d(Engine<T>& e, cx<T>* a, i64 nslices, i64 N, bool inverse, bool 
 template int fast_slice2d<double>(Engine<double>&, double2*, i64, i64, bool, bool, double, int, int, void* const*, bool*);
 template int fast_slice2d<float>(Engine<float>&, float2*, i64, i64, bool, bool, float, int, int, void* const*, bool*);
 
-int peer_barrier(Ctx* ctx, cudaStream_t st, void* const* flag_ptrs, int nranks, int rank, long long epoch) {
+// smallest column window granularity the fused exchange supports for R-point columns (0: no fused kernel)
+template <typename T> int fast_scatter_width(i64 R, i64 Cn) {
+  if (!is_pow2(R)) return 0;
+  const int logn = ilog2(R);
+  for (auto& f : scatter_registry<T>())
+    if (f.logn == logn && Cn % f.W == 0) return f.W;
+  return 0;
+}
+template int fast_scatter_width<double>(i64, i64);
+template int fast_scatter_width<float>(i64, i64);
+
+int peer_barrier(Ctx* ctx, cudaStream_t st, void* const* flag_ptrs, int nranks, int rank, long long epoch, int what) {
   if (nranks < 1 || nranks > 8) { set_error("1..8 ranks"); return ST_ARG; }
   PeerFlags pf;
   for (int h = 0; h < 8; ++h) pf.f[h] = h < nranks ? (long long*)flag_ptrs[h] : nullptr;
   JTB_TRY(ctx->ensure_watchdog());   // per-device flag; a time-out surfaces through Ctx::check_watchdog
-  JTB_LAUNCH(peer_barrier_kernel, 1u, 32u, 0, st, pf, nranks, rank, epoch, ctx->wd_dev);
+  JTB_LAUNCH(peer_barrier_kernel, 1u, 32u, 0, st, pf, nranks, rank, epoch, ctx->wd_dev, what);
   JTB_CUDA(cudaGetLastError());
   ctx->launches++;
   return ST_OK;
 }
 
-template int fast_scatter<double>(Engine<double>&, const double2*, i64, i64, i64, int, int, void* const*, bool, i64, bool);
-template int fast_scatter<float>(Engine<float>&, const float2*, i64, i64, i64, int, int, void* const*, bool, i64, bool);
+template int fast_scatter<double>(Engine<double>&, const double2*, i64, i64, i64, int, int, void* const*, bool, i64, bool, i64, i64);
+template int fast_scatter<float>(Engine<float>&, const float2*, i64, i64, i64, int, int, void* const*, bool, i64, bool, i64, i64);
 // true when a lean strided kernel exists for 2^logn-point lines in groups of c0 adjacent lines
 template <typename T> bool fast_has_strided(int logn, i64 c0) {
   for (auto& f : registry<T>())

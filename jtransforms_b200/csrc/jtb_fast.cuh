@@ -294,6 +294,10 @@ template <typename T> struct ScatterParams {
   // inverse re-slabbing (one [S][Rh*C] "slice", owner layout [Ls][R][C]): rl*P + g  ->  row_base = g, row_mul = P
   long long row_base;
   int row_ls_mul, row_mul;
+  // column window of this launch (the pipelined exchange sends the slab column block by column block so that the
+  // slice-axis pass of a block can start as soon as that block has arrived from every peer): columns
+  // [col0, col0 + groups*W) of every local slice
+  int col0, groups;
 };
 
 template <typename T, int LOGN, int LOGE, int W>
@@ -309,9 +313,9 @@ fft_scatter_kernel(const ScatterParams<T> p) {
   const int tid = threadIdx.x;
   const int w = tid % W, t = tid / W;
   for (int i = tid; i < FastTw<S>::COUNT_SM; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
-  const int groups = p.C / W;                       // column groups per slice
+  const int groups = p.groups;                      // column groups per slice in this launch's window
   const int ls = blockIdx.x / groups;
-  const int c = (blockIdx.x - ls * groups) * W + w;
+  const int c = p.col0 + (blockIdx.x - ls * groups) * W + w;
   const C* src = p.a + (i64)ls * S::N * p.C + c;
   C v[S::E];
 #pragma unroll
@@ -458,22 +462,27 @@ __global__ void __launch_bounds__(W * Sched<LOGN, LOGE>::TPL, 2) fft_slice2d_ker
 // cross-GPU barrier: thread h publishes `epoch` into rank h's flag array (slot = my rank) and waits until
 // rank h has published it into mine.  flags are peer-mapped int64[nranks] arrays, monotonically increasing.
 struct PeerFlags { long long* f[8]; };
-static __global__ void peer_barrier_kernel(const PeerFlags flags, int nranks, int rank, long long epoch, int* err) {
+// what = 1: publish only (signal), 2: wait only, 3: both (barrier)
+static __global__ void peer_barrier_kernel(const PeerFlags flags, int nranks, int rank, long long epoch, int* err, int what) {
 #ifndef JTB_EMU
   const int h = threadIdx.x;
   if (h >= nranks) return;
-  __threadfence_system();
-  volatile long long* theirs = flags.f[h] + rank;
-  *theirs = epoch;
-  __threadfence_system();
-  volatile long long* mine = flags.f[rank] + h;
-  unsigned long long t0, t1;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  while (*mine < epoch) {
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    if (t1 - t0 > 10000000000ULL) { *err = 2; break; }   // 10 s: a peer died; give up instead of hanging the GPU
+  if (what & 1) {
+    __threadfence_system();
+    volatile long long* theirs = flags.f[h] + rank;
+    *theirs = epoch;
+    __threadfence_system();
   }
-  __threadfence_system();
+  if (what & 2) {
+    volatile long long* mine = flags.f[rank] + h;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (*mine < epoch) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 10000000000ULL) { *err = 2; break; }   // 10 s: a peer died; give up instead of hanging the GPU
+    }
+    __threadfence_system();
+  }
 #endif
 }
 

@@ -34,6 +34,10 @@ template <> std::vector<F2Entry<double>>& reg2<double>() {
       // first pass of the two-pass transform (strided lines, twiddle at the store)
       mk2<double, 6, 3, true, FM_TWID, 32>(), mk2<double, 7, 4, true, FM_TWID, 16>(), mk2<double, 8, 4, true, FM_TWID, 8>(),
       mk2<double, 9, 3, true, FM_TWID, 8>(), mk2<double, 10, 4, true, FM_TWID, 8>(),
+      // half-width variants for launches that would not fill the GPU otherwise (a single 2^20-point transform is
+      // 1024 lines: 128 CTAs at W = 8, 256 at W = 4) -- find2 picks by CTA count
+      mk2<double, 9, 3, true, FM_TWID, 4>(), mk2<double, 10, 4, true, FM_TWID, 4>(),
+      mk2<double, 9, 3, false, FM_TRANSPOSE, 4>(), mk2<double, 10, 4, false, FM_TRANSPOSE, 4>(),
       // second pass, contiguous lines with transposed store
       mk2<double, 8, 4, false, FM_TRANSPOSE, 8>(), mk2<double, 9, 3, false, FM_TRANSPOSE, 8>(),
       mk2<double, 10, 4, false, FM_TRANSPOSE, 8>(),
@@ -61,10 +65,20 @@ template <> std::vector<F2Entry<float>>& reg2<float>() {
   return r;
 }
 
+// variant for `lines` lines: the widest one (most lines per CTA, longest segments) that still gives every SM two CTAs;
+// when none does, the narrowest (most CTAs).  JTB_FS_W forces a width where it exists.
 template <typename T> F2Entry<T>* find2(int logn, bool sin, int mode, i64 lines = (1LL << 60)) {
-  for (auto& f : reg2<T>())
-    if (f.logn == logn && (f.sin != 0) == sin && f.mode == mode && lines >= f.min_lines) return &f;
-  return nullptr;
+  static const int force_w = getenv("JTB_FS_W") ? atoi(getenv("JTB_FS_W")) : 0;
+  F2Entry<T>*wide = nullptr, *narrow = nullptr, *forced = nullptr;
+  for (auto& f : reg2<T>()) {
+    if (f.logn != logn || (f.sin != 0) != sin || f.mode != mode || lines < f.min_lines) continue;
+    if (mode != FM_TWID && mode != FM_TRANSPOSE) return &f;   // the other families list their default first
+    if (force_w && f.W == force_w) forced = &f;
+    if ((lines + f.W - 1) / f.W >= 2 * 148 && (!wide || f.W > wide->W)) wide = &f;
+    if (!narrow || f.W < narrow->W) narrow = &f;
+  }
+  if (forced) return forced;
+  return wide ? wide : narrow;
 }
 
 template <typename T> int launch2(Engine<T>& e, F2Entry<T>* f, Fast2Params<T>& p) {
@@ -107,6 +121,12 @@ int fast_fourstep_contig(Engine<T>& e, const cx<T>* in, i64 in_dist, cx<T>* out,
   if (g_fast2_off || l1 <= l0) return ST_OK;
   // split n = N1 (strided first pass) * N2 (contiguous second pass)
   F2Entry<T>*f1 = nullptr, *f2 = nullptr;
+  static const int force_la = getenv("JTB_FS_LA") ? atoi(getenv("JTB_FS_LA")) : 0;   // log2 of the first-pass length
+  if (force_la > 0 && force_la < logn) {
+    F2Entry<T>* x = find2<T>(force_la, true, FM_TWID, (l1 - l0) << (logn - force_la));
+    F2Entry<T>* y = find2<T>(logn - force_la, false, FM_TRANSPOSE, (l1 - l0) << force_la);
+    if (x && y) { f1 = x; f2 = y; }
+  }
   for (int la = logn / 2; la >= 6 && !f1; --la) {
     for (int s = 0; s < 2 && !f1; ++s) {
       const int a = s == 0 ? la : logn - la;   // try the balanced split first, then its mirror

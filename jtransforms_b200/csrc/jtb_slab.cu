@@ -132,9 +132,24 @@ struct jtb_slab {
   int step = 0;
   int exchange = 0;                      // 0 peer stores, 1 NCCL
   void* comm = nullptr;
+  // pipelined exchange (forward, fused peer stores): the slab is sent column block by column block and the slice-axis
+  // pass of block j runs on `st2` as soon as block j has arrived from every peer, under the stores of blocks j+1..
+  int nchunks = 1;                       // column blocks per step (JTB_SLAB_CHUNKS; 1 = one exchange, then the k1 pass)
+  cudaStream_t st2 = nullptr;            // high-priority stream of the consumer side
+  cudaEvent_t evc[16];                   // same-process groups: block j of this member has been stored
+  cudaEvent_t ev_join = nullptr;
+  long long chunk_epoch[16];             // IPC peers: flag value that announces block j of the current step
   // optional phase timing (jtb_slab_profile): events at the phase boundaries of the last step on its stream
   bool profile = false;
   cudaEvent_t pev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t pev_s[16], pev_k[16];      // pipelined step: block j stored (producer stream) / block j transformed (consumer)
+  int last_nb = 0;
+  int mark_chunk(cudaEvent_t* arr, int j, cudaStream_t st) {
+    if (!profile) return ST_OK;
+    if (!arr[j]) JTB_CUDA(cudaEventCreate(&arr[j]));
+    JTB_CUDA(cudaEventRecord(arr[j], st));
+    return ST_OK;
+  }
   int mark(int i, cudaStream_t st) {
     if (!profile) return ST_OK;
     if (!pev[i]) JTB_CUDA(cudaEventCreate(&pev[i]));
@@ -146,6 +161,10 @@ struct jtb_slab {
     memset(peer_flags, 0, sizeof peer_flags);
     memset(ipc_open, 0, sizeof ipc_open);
     memset(group, 0, sizeof group);
+    memset(evc, 0, sizeof evc);
+    memset(pev_s, 0, sizeof pev_s);
+    memset(pev_k, 0, sizeof pev_k);
+    memset(chunk_epoch, 0, sizeof chunk_epoch);
   }
 };
 
@@ -253,6 +272,72 @@ template <typename T> int slab_back_b(jtb_slab* m, cx<T>* loc, bool scale, cudaS
   return e.c2c_lines(loc, geo_contig(Cn), Ls * R, Cn, true, scale, (T)(1.0 / ((double)m->S * (double)R * (double)Cn)));
 }
 
+// ---- pipelined forward step: column blocks of the exchange overlap the slice-axis pass (see jtb_slab::nchunks)
+// number of column blocks this member's shape supports (1: not pipelined)
+template <typename T> int slab_pipe_blocks(const jtb_slab* m) {
+  if (m->P < 2 || m->exchange != 0 || m->nchunks < 2 || !is_pow2(m->S)) return 1;
+  const int w = fast_scatter_width<T>(m->R, m->Cn);
+  if (w <= 0) return 1;
+  int nb = m->nchunks > 16 ? 16 : m->nchunks;
+  for (; nb > 1; --nb) {
+    if (m->Cn % nb) continue;
+    const i64 cc = m->Cn / nb;
+    if (cc % w == 0 && fast_has_strided<T>(ilog2(m->S), cc)) break;
+  }
+  return nb;
+}
+int slab_pipe_ensure(jtb_slab* m, int nb) {
+  if (!m->st2) {
+    int lo = 0, hi = 0;
+    JTB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    static const char* ep = getenv("JTB_PIPE_PRIO");   // 0: consumer stream at normal priority
+    JTB_CUDA(cudaStreamCreateWithPriority(&m->st2, cudaStreamNonBlocking, (ep && atoi(ep) == 0) ? lo : hi));
+    JTB_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+  }
+  for (int j = 0; j < nb; ++j)
+    if (!m->evc[j]) JTB_CUDA(cudaEventCreateWithFlags(&m->evc[j], cudaEventDisableTiming));
+  return ST_OK;
+}
+// producer side on `st`: rows in place, then the column (k2) pass block by block, its stores going to the owners;
+// every block is announced (event for same-process groups, flag write for IPC peers)
+template <typename T> int slab_pipe_produce(jtb_slab* m, cx<T>* a, bool inverse, cudaStream_t st, int buf, int nb) {
+  Engine<T> e(m->ctx, st);
+  const i64 Ls = m->Ls, R = m->R, Cn = m->Cn, cc = Cn / nb;
+  JTB_TRY(slab_pipe_ensure(m, nb));
+  JTB_TRY(e.c2c_lines(a, geo_contig(Cn), Ls * R, Cn, inverse, false, (T)1));
+  for (int j = 0; j < nb; ++j) {
+    JTB_TRY(fast_scatter<T>(e, a, Ls, R, Cn, m->P, m->rank, m->peer_recv[buf], inverse, -1, false, (i64)j * cc, cc));
+    if (m->mode == 1) {
+      m->chunk_epoch[j] = ++m->epoch;
+      JTB_TRY(peer_barrier(m->ctx, st, (void* const*)m->peer_flags, m->P, m->rank, m->epoch, 1));
+    } else {
+      JTB_CUDA(cudaEventRecord(m->evc[j], st));
+    }
+    JTB_TRY(m->mark_chunk(m->pev_s, j, st));
+  }
+  m->last_nb = nb;
+  return ST_OK;
+}
+// consumer side on `st2`: block j of the re-slabbed array [S][Rh][C] once every peer has announced it; `st` joins at the end
+template <typename T> int slab_pipe_consume(jtb_slab* m, bool inverse, bool scale, cudaStream_t st, int buf, int nb) {
+  Engine<T> e2(m->ctx, m->st2);
+  const i64 S = m->S, Rh = m->Rh, Cn = m->Cn, cc = Cn / nb;
+  const T sc = (T)(1.0 / ((double)S * (double)m->R * (double)Cn));
+  for (int j = 0; j < nb; ++j) {
+    if (m->mode == 1) {
+      JTB_TRY(peer_barrier(m->ctx, m->st2, (void* const*)m->peer_flags, m->P, m->rank, m->chunk_epoch[j], 2));
+    } else {
+      for (int h = 0; h < m->P; ++h) JTB_CUDA(cudaStreamWaitEvent(m->st2, m->group[h]->evc[j], 0));
+    }
+    cx<T>* b = (cx<T>*)m->recv[buf] + (i64)j * cc;
+    JTB_TRY(e2.c2c_lines(b, geo_make(cc, 1, Cn, Rh * Cn), Rh * cc, S, inverse, scale, sc));
+    JTB_TRY(m->mark_chunk(m->pev_k, j, m->st2));
+  }
+  JTB_CUDA(cudaEventRecord(m->ev_join, m->st2));
+  JTB_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0));
+  return ST_OK;
+}
+
 int slab_check_buffers(jtb_slab* m) {
   if (m->P > 1 && (m->mode == 0 || !m->recv[0])) { set_error("slab member is not connected to its peers"); return ST_ARG; }
   return ST_OK;
@@ -298,6 +383,30 @@ int slab_group_run(jtb_slab* const* ms, int n, void* const* a, bool back, bool i
     JTB_TRY(slab_check_buffers(ms[g]));
   }
   const int buf = ms[0]->step & 1;
+  const int nb = back ? 1 : (f64 ? slab_pipe_blocks<double>(ms[0]) : slab_pipe_blocks<float>(ms[0]));
+  if (nb > 1) {
+    for (int g = 0; g < n; ++g) {
+      jtb_slab* m = ms[g];
+      DeviceGuard dg(m->device);
+      JTB_TRY(m->ctx->order_begin(st[g]));
+      JTB_TRY(m->mark(0, st[g]));
+      JTB_TRY(f64 ? slab_pipe_produce<double>(m, (double2*)a[g], inverse, st[g], buf, nb)
+                  : slab_pipe_produce<float>(m, (float2*)a[g], inverse, st[g], buf, nb));
+      JTB_TRY(m->mark(1, st[g]));
+      JTB_TRY(m->mark(2, st[g]));
+    }
+    for (int g = 0; g < n; ++g) {
+      jtb_slab* m = ms[g];
+      DeviceGuard dg(m->device);
+      JTB_TRY(f64 ? slab_pipe_consume<double>(m, inverse, scale, st[g], buf, nb)
+                  : slab_pipe_consume<float>(m, inverse, scale, st[g], buf, nb));
+      JTB_TRY(m->mark(3, st[g]));
+      JTB_TRY(m->ctx->order_end(st[g]));
+      results[g] = m->recv[buf];
+      m->step++;
+    }
+    return ST_OK;
+  }
   bool exchanged[8] = {false};
   for (int g = 0; g < n; ++g) {
     jtb_slab* m = ms[g];
@@ -384,6 +493,13 @@ int jtb_slab_create(jtb_slab** out, int prec, int64_t S, int64_t R, int64_t Cn, 
   {
     static const char* ex = getenv("JTB_EXCHANGE_NCCL");
     m->exchange = (ex && atoi(ex)) ? 1 : 0;
+    static const char* ch = getenv("JTB_SLAB_CHUNKS");
+    // Measured on 2 x B200, 512^3 (profiles/r02_pipe_timeline_2gpu.log): the blocks do overlap, but the peer-store
+    // exchange needs every SM's store slots -- a block's stores take 0.20 ms alone and 0.31 ms next to the slice-axis
+    // pass of the previous block (0.10 ms alone), so the step is 1.56 ms against 1.28 ms for the fused in-slice kernel +
+    // one barrier.  Off by default; JTB_SLAB_CHUNKS=2..16 switches the pipelined variant on.
+    m->nchunks = ch ? atoi(ch) : 1;
+    if (m->nchunks < 1) m->nchunks = 1;
   }
   if (nranks > 1) {
     cudaError_t e = cudaMalloc(&m->recv[0], m->block_bytes);
@@ -418,6 +534,13 @@ int jtb_slab_destroy(jtb_slab* m) {
   for (int b = 0; b < 2; ++b) if (m->recv[b]) cudaFree(m->recv[b]);
   if (m->flags) cudaFree(m->flags);
   if (m->ev) cudaEventDestroy(m->ev);
+  if (m->st2) cudaStreamDestroy(m->st2);
+  if (m->ev_join) cudaEventDestroy(m->ev_join);
+  for (int j = 0; j < 16; ++j) {
+    if (m->evc[j]) cudaEventDestroy(m->evc[j]);
+    if (m->pev_s[j]) cudaEventDestroy(m->pev_s[j]);
+    if (m->pev_k[j]) cudaEventDestroy(m->pev_k[j]);
+  }
   for (int i = 0; i < 4; ++i) if (m->pev[i]) cudaEventDestroy(m->pev[i]);
   cudaGetLastError();
   delete m;
@@ -573,6 +696,22 @@ static int slab_member_run(jtb_slab* m, void* a, bool back, bool inverse, bool s
   JTB_TRY(slab_check_buffers(m));
   JTB_TRY(m->ctx->order_begin(st));
   const int buf = m->step & 1;
+  {
+    const int nb = back ? 1 : (f64 ? slab_pipe_blocks<double>(m) : slab_pipe_blocks<float>(m));
+    if (nb > 1) {
+      JTB_TRY(m->mark(0, st));
+      JTB_TRY(f64 ? slab_pipe_produce<double>(m, (double2*)a, inverse, st, buf, nb)
+                  : slab_pipe_produce<float>(m, (float2*)a, inverse, st, buf, nb));
+      JTB_TRY(m->mark(1, st));
+      JTB_TRY(m->mark(2, st));
+      m->step++;
+      JTB_TRY(f64 ? slab_pipe_consume<double>(m, inverse, scale, st, buf, nb) : slab_pipe_consume<float>(m, inverse, scale, st, buf, nb));
+      JTB_TRY(m->mark(3, st));
+      JTB_TRY(m->ctx->order_end(st));
+      *result = m->recv[buf];
+      return ST_OK;
+    }
+  }
   bool exchanged = false;
   JTB_TRY(m->mark(0, st));
   if (back) JTB_TRY(f64 ? slab_back_a<double>(m, (double2*)a, st, buf, &exchanged) : slab_back_a<float>(m, (float2*)a, st, buf, &exchanged));
@@ -642,6 +781,24 @@ int jtb_slab_last_times(jtb_slab* m, float* ms3) {
   DeviceGuard dg(m->device);
   JTB_CUDA(cudaEventSynchronize(m->pev[3]));
   for (int i = 0; i < 3; ++i) JTB_CUDA(cudaEventElapsedTime(&ms3[i], m->pev[i], m->pev[i + 1]));
+  return ST_OK;
+}
+
+// timeline of the last profiled PIPELINED step, ms since its start: stored[j] = column block j has left (producer
+// stream), done[j] = slice-axis pass of block j finished (consumer stream).  Returns the number of blocks (0: the last
+// step was not pipelined) in *nblocks; arrays hold up to 16 entries.
+int jtb_slab_chunk_times(jtb_slab* m, int* nblocks, float* stored, float* done) {
+  if (!m || !nblocks || !stored || !done) { set_error("null argument"); return ST_ARG; }
+  *nblocks = 0;
+  if (!m->profile || !m->pev[0] || m->last_nb < 2) return ST_OK;
+  DeviceGuard dg(m->device);
+  JTB_CUDA(cudaEventSynchronize(m->pev[3]));
+  for (int j = 0; j < m->last_nb; ++j) {
+    if (!m->pev_s[j] || !m->pev_k[j]) return ST_OK;
+    JTB_CUDA(cudaEventElapsedTime(&stored[j], m->pev[0], m->pev_s[j]));
+    JTB_CUDA(cudaEventElapsedTime(&done[j], m->pev[0], m->pev_k[j]));
+  }
+  *nblocks = m->last_nb;
   return ST_OK;
 }
 

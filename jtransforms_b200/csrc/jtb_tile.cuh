@@ -224,13 +224,14 @@ __global__ void __launch_bounds__(Sched<LOGN, LOGE>::MAXT, (Sched<LOGN, LOGE>::M
       for (int q = 0; q < S::E; ++q) {
         const int k = t + q * S::TPL;
         const i64 e = ebase + k * p.lout_ks;
+        if (p.valid_out >= 0 && e >= p.valid_out) continue;   // truncated output: neither stored nor looked up (postmul has valid_out entries)
         C z = v[q];
         if (p.swap_out1) z = cswap(z);
         if (p.fs_mode) z = cmul(z, fs_twiddle(p, fidx * k));
         if (p.postmul) { C m = __ldg(p.postmul + e); z = p.postmul_conj ? cmulc(z, m) : cmul(z, m); }
         if (p.has_scale) { z.x *= p.scale; z.y *= p.scale; }
         if (p.swap_out) z = cswap(z);
-        if (p.valid_out < 0 || e < p.valid_out) dst[k * st] = z;
+        dst[k * st] = z;
       }
     }
   } else {

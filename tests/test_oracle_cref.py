@@ -32,3 +32,23 @@ def test_cref_inverse_and_nd():
         cref.cfft3d(a, S, R, Cn, -1, 3)
         want = o.complex_forward_3d(x, S, R, Cn) if S > 1 else o.complex_forward_2d(x, R, Cn)
         assert o.rel_l2(a, want) < 1e-12 * 20
+
+
+def test_cref_real2d_r2r_bluestein():
+    """the CPU-baseline drivers of configs 2, 3 and 4 compute what the oracle says"""
+    for (R, Cn) in [(8, 16), (64, 32), (128, 256)]:
+        x = o.fill_uniform(R * Cn, seed=6, lo=-1.0, hi=1.0)
+        a = x.copy()
+        cref.rfft2d(a, R, Cn, 3)
+        assert o.rel_l2(a, o.real_forward_2d(x, R, Cn)) < 1e-12 * 20
+        for kind, want in (("dct", o.dct_forward_nd(x, (R, Cn), True)), ("dst", o.dst_forward_nd(x, (R, Cn), True)),
+                           ("dht", o.dht_forward_nd(x, (R, Cn)))):
+            b = x.copy()
+            cref.r2r2d(b, R, Cn, kind, 3)
+            assert o.rel_l2(b, want) < 1e-12 * 20, kind
+    n, nb = 1009, 3
+    x = o.fill_uniform(2 * n * nb, seed=8, lo=-1.0, hi=1.0).astype(np.float32)
+    a = x.copy()
+    cref.bluestein_f32(a, n, nb, 2)
+    want = np.concatenate([o.complex_forward_1d(x[2 * n * i:2 * n * (i + 1)].astype(np.float64), n) for i in range(nb)])
+    assert o.rel_l2(a.astype(np.float64), want) < 1e-5 * 10
