@@ -221,6 +221,11 @@ template <typename T> int nd_r2r(Engine<T>& e, T* a, int kind, int rank, const i
   if (rank == 2) {
     const i64 R = d[0], Cn = d[1];
     JTB_TRY(e.r2r_lines(a, geo_make(Cn, 1, R * Cn, Cn), Cn, R, kind, inverse, scale));
+    if (kind == JTB_DHT) {   // rows + yTransform in one pass (row pairs r, R-r per CTA)
+      bool folded = false;
+      JTB_TRY(fast_dht2d_rows<T>(e, a, R, Cn, (inverse && scale) ? (T)(1.0 / (double)Cn) : (T)1, &folded));
+      if (folded) return ST_OK;
+    }
     JTB_TRY(e.r2r_lines(a, geo_contig(Cn), R, Cn, kind, inverse, scale));
     if (kind == JTB_DHT) {
       grid_for((R / 2 + 1) * (Cn / 2 + 1), &g, &b);

@@ -168,6 +168,7 @@ int fast_threepass_contig(Engine<T>& e, cx<T>* a, i64 dist, i64 l0, i64 l1, int 
 template <typename T> int fast_rfft_fwd(Engine<T>& e, cx<T>* a, i64 dist, i64 nlines, int logN, bool* handled);
 template <typename T>
 int fast_r2r_rows(Engine<T>& e, T* a, i64 dist, i64 nlines, i64 n, int kind, T f0, T f, bool* handled);
+template <typename T> int fast_dht2d_rows(Engine<T>& e, T* a, i64 R, i64 n, T f, bool* handled);   // jtb_fast2.cu
 template <typename T>
 int fast_r2r_cols(Engine<T>& e, T* a, i64 n, i64 Cn, i64 batches, i64 bdist, int kind, T f0, T f, bool* handled);
 template <typename T>
@@ -188,6 +189,9 @@ int fast_slice2d(Engine<T>& e, cx<T>* a, i64 nslices, i64 N, bool inverse, bool 
 template <typename T>
 int mixed_c2c(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, i64 n, bool inverse, bool has_scale, T scale,
               bool* handled);   // jtb_mixed.cu
+template <typename T>
+int mixed_twopass_contig(Engine<T>& e, cx<T>* a, i64 dist, i64 nlines, i64 n, bool inverse, bool has_scale, T scale,
+                         bool* handled);   // jtb_mixed.cu
 // what: 1 publish `epoch` to every peer, 2 wait until every peer has published it, 3 both (barrier)
 int peer_barrier(Ctx* ctx, cudaStream_t st, void* const* flag_ptrs, int nranks, int rank, long long epoch, int what = 3);
 

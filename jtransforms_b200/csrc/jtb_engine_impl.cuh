@@ -425,6 +425,9 @@ int Engine<T>::c2c_lines(C* a, const Geo& g, i64 nlines, i64 n, bool inverse, bo
   // Bluestein chirp-z (fft/DoubleFFT_1D.java:1920-2107); inverse = swap . forward . swap
   if (g.stride == 1 && g.c[0] == 1 && g.c[1] == 1 && g.c[2] == 1) {
     bool handled = false;
+    // long smooth lengths: two mixed-radix passes (n = N1*N2)
+    JTB_TRY(mixed_twopass_contig<T>(*this, a, g.d[3], nlines, n, inverse, has_scale, scale, &handled));
+    if (handled) return ST_OK;
     JTB_TRY(fast_bluestein_contig<T>(*this, a, g.d[3], nlines, n, inverse, has_scale, scale, &handled));
     if (handled) return ST_OK;
   }

@@ -195,29 +195,34 @@ int fast_fourstep_strided(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, int 
   JTB_TRY(e.fs_tables(logn, &fsA, &fsB, &logL));
   // Column strips small enough that the intermediate written by pass 1 is still in L2 (126 MB) when pass 2
   // reads it: the two passes then cost about one sweep of HBM traffic instead of two.
+  // (every strip reuses the same compact [n][cb] work block: see fast_r2r_cols)
   i64 cb = g.c[0];
   {
-    const char* ev = getenv("JTB_STRIP_MB");
-    const double strip_mb = ev ? atof(ev) : 1.0e9;   // off by default: measured slower (launch-bound strips)
+    const char* ev = getenv("JTB_C2C_STRIP_MB") ? getenv("JTB_C2C_STRIP_MB") : getenv("JTB_STRIP_MB");
+    const double strip_mb = ev ? atof(ev) : 0.0;
     const i64 wmax = f1->W > f2->W ? f1->W : f2->W;
-    while (cb > wmax && (cb % 2) == 0 && (double)cb * (double)n * batches * sizeof(C) > strip_mb * 1048576.0) cb /= 2;
+    if (strip_mb > 0)
+      while (cb > wmax && (cb % 2) == 0 && (double)cb * (double)n * batches * sizeof(C) > strip_mb * 1048576.0) cb /= 2;
     if (cb % f1->W || cb % f2->W) cb = g.c[0];
   }
+  const bool compact = cb < g.c[0];
+  const i64 ws = compact ? cb : s, wbd = compact ? n * cb : g.d[3];   // row / batch distance inside the work block
   for (i64 cs = 0; cs < g.c[0]; cs += cb) {
-    // pass 1: lines (c, r2, batch): FFT over r1 (element stride R2*s), twiddle W_n^(k1*r2), a -> work (same offsets)
+    C* wks = compact ? wk : wk + cs;
+    // pass 1: lines (c, r2, batch): FFT over r1 (element stride R2*s), twiddle W_n^(k1*r2), a -> work
     Fast2Params<T> p = blank2<T>();
-    p.in = a + cs; p.out = wk + cs;
+    p.in = a + cs; p.out = wks;
     p.nlines = cb * R2 * batches; p.c0 = (int)cb; p.gmod = (int)R2;
     p.in_gdist = s; p.in_gdist2 = g.d[3]; p.in_cdist = 1; p.in_stride = R2 * s;
-    p.out_gdist = s; p.out_gdist2 = g.d[3]; p.out_cdist = 1; p.out_stride = R2 * s;
+    p.out_gdist = ws; p.out_gdist2 = wbd; p.out_cdist = 1; p.out_stride = R2 * ws;
     p.swap_in = inverse;
     p.fsA = fsA; p.fsB = fsB; p.fs_logL = logL; p.tw_src = 1;
     JTB_TRY(launch2(e, f1, p));
     // pass 2: lines (c, k1, batch): FFT over r2 (rows k1*R2 + r2), output element k2 -> row k1 + R1*k2, work -> a
     Fast2Params<T> q = blank2<T>();
-    q.in = wk + cs; q.out = a + cs;
+    q.in = wks; q.out = a + cs;
     q.nlines = cb * R1 * batches; q.c0 = (int)cb; q.gmod = (int)R1;
-    q.in_gdist = R2 * s; q.in_gdist2 = g.d[3]; q.in_cdist = 1; q.in_stride = s;
+    q.in_gdist = R2 * ws; q.in_gdist2 = wbd; q.in_cdist = 1; q.in_stride = ws;
     q.out_gdist = s; q.out_gdist2 = g.d[3]; q.out_cdist = 1; q.out_stride = R1 * s;
     q.swap_out = inverse; q.has_scale = has_scale; q.scale = scale;
     JTB_TRY(launch2(e, f2, q));
@@ -351,13 +356,14 @@ template <typename T, int LOGN, int LOGE, int KIND, int W> RowEntry<T> mkrow() {
 #define JTB_ROWS(T, LOGN, LOGE, W) mkrow<T, LOGN, LOGE, RK_DCT, W>(), mkrow<T, LOGN, LOGE, RK_DST, W>(), mkrow<T, LOGN, LOGE, RK_DHT, W>()
 template <typename T> std::vector<RowEntry<T>>& rowreg();
 template <> std::vector<RowEntry<double>>& rowreg<double>() {
-  static std::vector<RowEntry<double>> r = {JTB_ROWS(double, 12, 4, 1), JTB_ROWS(double, 12, 3, 1), JTB_ROWS(double, 11, 3, 1), JTB_ROWS(double, 11, 4, 2), JTB_ROWS(double, 10, 3, 2),
+  static std::vector<RowEntry<double>> r = {mkrow<double, 12, 4, RK_DHT, 2>(),   // row pairs (fast_dht2d_rows); plain rows skip it (W = 1 first)
+                                            JTB_ROWS(double, 12, 4, 1), JTB_ROWS(double, 12, 3, 1), JTB_ROWS(double, 11, 3, 1), JTB_ROWS(double, 11, 4, 2), JTB_ROWS(double, 10, 3, 2),
                                             JTB_ROWS(double, 9, 3, 4), JTB_ROWS(double, 8, 4, 8), JTB_ROWS(double, 7, 4, 16),
                                             JTB_ROWS(double, 6, 3, 16), JTB_ROWS(double, 5, 3, 32)};
   return r;
 }
 template <> std::vector<RowEntry<float>>& rowreg<float>() {
-  static std::vector<RowEntry<float>> r = {JTB_ROWS(float, 12, 4, 1), JTB_ROWS(float, 11, 4, 2), JTB_ROWS(float, 10, 4, 4),
+  static std::vector<RowEntry<float>> r = {mkrow<float, 12, 4, RK_DHT, 2>(), JTB_ROWS(float, 12, 4, 1), JTB_ROWS(float, 11, 4, 2), JTB_ROWS(float, 10, 4, 4),
                                            JTB_ROWS(float, 9, 3, 8),  JTB_ROWS(float, 8, 4, 16), JTB_ROWS(float, 7, 4, 16),
                                            JTB_ROWS(float, 6, 3, 32), JTB_ROWS(float, 5, 3, 32)};
   return r;
@@ -427,15 +433,16 @@ int fast_r2r_rows(Engine<T>& e, T* a, i64 dist, i64 nlines, i64 n, int kind, T f
   RowEntry<T>* r = nullptr;
   static const char* ele = getenv("JTB_ROW_LOGE");   // tuning knob: prefer the variant with this radix
   const int want_loge = ele ? atoi(ele) : 0;
-  for (auto& x : rowreg<T>()) if (x.logn == logN && x.kind == kind && (!want_loge || x.loge == want_loge)) { r = &x; break; }
-  if (!r) for (auto& x : rowreg<T>()) if (x.logn == logN && x.kind == kind) { r = &x; break; }
+  const auto pair_only = [](const RowEntry<T>& x) { return x.logn == 12 && x.W == 2; };   // registered for fast_dht2d_rows
+  for (auto& x : rowreg<T>()) if (x.logn == logN && x.kind == kind && !pair_only(x) && (!want_loge || x.loge == want_loge)) { r = &x; break; }
+  if (!r) for (auto& x : rowreg<T>()) if (x.logn == logN && x.kind == kind && !pair_only(x)) { r = &x; break; }
   if (!r) return ST_OK;
   if (!(r->attr_done & (1u << (e.ctx->device & 31)))) {
     JTB_CUDA(cudaFuncSetAttribute(r->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, r->smem));
     r->attr_done |= 1u << (e.ctx->device & 31);
   }
   RowR2RParams<T> p;
-  p.a = a; p.nlines = nlines; p.dist = dist; p.f0 = f0; p.f = f;
+  p.a = a; p.nlines = nlines; p.dist = dist; p.f0 = f0; p.f = f; p.pair_rows = 0;
   JTB_TRY(fast_stage_table<T>(e, logN, r->loge, &p.twg));
   const cx<T>* tw[JTB_MAX_STAGES];
   JTB_TRY(e.tile_tables(logN, tw, &p.rtw));
@@ -449,6 +456,40 @@ int fast_r2r_rows(Engine<T>& e, T* a, i64 dist, i64 nlines, i64 n, int kind, T f
   *handled = true;
   return ST_OK;
 }
+
+// Last pass of DoubleDHT_2D.forward / inverse on one R x n array: the row DHTs with yTransform
+// (dht/DoubleDHT_2D.java:1288-1309) folded into the store -- a CTA owns the row pairs (r, R - r), so the separate
+// yTransform sweep (one more read + write of the array) disappears.
+template <typename T>
+int fast_dht2d_rows(Engine<T>& e, T* a, i64 R, i64 n, T f, bool* handled) {
+  *handled = false;
+  static const bool off = getenv("JTB_NO_DHTFOLD") != nullptr;
+  if (g_fast2_off || off || R < 2 || (R % 2) || !is_pow2(n) || n < 4 || ((uintptr_t)a % sizeof(cx<T>))) return ST_OK;
+  const int logN = ilog2(n) - 1;
+  RowEntry<T>* r = nullptr;
+  for (auto& x : rowreg<T>()) if (x.logn == logN && x.kind == RK_DHT && x.W >= 2 && (x.W % 2) == 0) { r = &x; break; }
+  if (!r) return ST_OK;
+  if (!(r->attr_done & (1u << (e.ctx->device & 31)))) {
+    JTB_CUDA(cudaFuncSetAttribute(r->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, r->smem));
+    r->attr_done |= 1u << (e.ctx->device & 31);
+  }
+  RowR2RParams<T> p;
+  p.a = a; p.nlines = R; p.dist = n; p.f0 = f; p.f = f; p.pair_rows = R;
+  JTB_TRY(fast_stage_table<T>(e, logN, r->loge, &p.twg));
+  const cx<T>* tw[JTB_MAX_STAGES];
+  JTB_TRY(e.tile_tables(logN, tw, &p.rtw));
+  p.dtw = nullptr;
+  const i64 pairs = R / 2, per = r->W / 2;
+  const i64 nblk = (pairs + per - 1) / per;
+  if (nblk > 0x7fffffffLL) return ST_OK;
+  JTB_LAUNCH(r->kern, (unsigned)nblk, (unsigned)r->threads, (size_t)r->smem, e.st, p);
+  JTB_CUDA(cudaGetLastError());
+  e.ctx->launches++;
+  *handled = true;
+  return ST_OK;
+}
+template int fast_dht2d_rows<double>(Engine<double>&, double*, i64, i64, double, bool*);
+template int fast_dht2d_rows<float>(Engine<float>&, float*, i64, i64, float, bool*);
 
 // forward DCT-II / DST-II / DHT along the strided axis of length n of `batches` row-major [n][Cn] real arrays
 // (batch distance bdist reals): two adjacent real columns = one complex column, two-pass complex FFT with the
@@ -485,20 +526,27 @@ int fast_r2r_cols(Engine<T>& e, T* a, i64 n, i64 Cn, i64 batches, i64 bdist, int
   int logL;
   JTB_TRY(e.fs_tables(logn, &fsA, &fsB, &logL));
   if (kind != RK_DHT) JTB_TRY(e.dct_table(n, &dtw));
+  // Column strips small enough that the intermediate written by the first pass is still in L2 when the second pass
+  // reads it; every strip reuses the SAME compact [n][cb] work block, so its dirty lines are overwritten in L2 instead
+  // of being written back: the two passes then cost one sweep of HBM traffic (JTB_STRIP_MB = strip size, 0 = off).
   i64 cb = H;
   {
-    const char* ev = getenv("JTB_STRIP_MB");
-    const double strip_mb = ev ? atof(ev) : 1.0e9;   // off by default: measured slower (launch-bound strips)
+    const char* ev = getenv("JTB_R2R_STRIP_MB") ? getenv("JTB_R2R_STRIP_MB") : getenv("JTB_STRIP_MB");
+    const double strip_mb = ev ? atof(ev) : 0.0;
     const i64 wmax = f1->W > f2->W ? f1->W : f2->W;
-    while (cb > wmax && (cb % 2) == 0 && (double)cb * (double)n * batches * sizeof(C) > strip_mb * 1048576.0) cb /= 2;
-    if (cb % f1->W || cb % f2->W) cb = H;
+    if (strip_mb > 0 && fp)
+      while (cb > wmax && (cb % 2) == 0 && (double)cb * (double)n * batches * sizeof(C) > strip_mb * 1048576.0) cb /= 2;
+    if (cb % f1->W || cb % f2->W || (fp && cb % fp->W)) cb = H;
   }
+  const bool compact = cb < H && fp;
+  const i64 ws = compact ? cb : s, wbd = compact ? n * cb : bd;   // row / batch distance inside the work block
   for (i64 cs = 0; cs < H; cs += cb) {
+    C* wks = compact ? wk : wk + cs;
     Fast2Params<T> p = blank2<T>();
-    p.in = ac + cs; p.out = wk + cs;
+    p.in = ac + cs; p.out = wks;
     p.nlines = cb * R2 * batches; p.c0 = (int)cb; p.gmod = (int)R2;
     p.in_gdist = s; p.in_gdist2 = bd; p.in_cdist = 1; p.in_stride = R2 * s;
-    p.out_gdist = s; p.out_gdist2 = bd; p.out_cdist = 1; p.out_stride = R2 * s;
+    p.out_gdist = ws; p.out_gdist2 = wbd; p.out_cdist = 1; p.out_stride = R2 * ws;
     p.fsA = fsA; p.fsB = fsB; p.fs_logL = logL; p.tw_src = 1;
     p.pre_n = n; p.pre_s = s;
     JTB_TRY(launch2(e, f1, p));
@@ -509,7 +557,7 @@ int fast_r2r_cols(Engine<T>& e, T* a, i64 n, i64 Cn, i64 batches, i64 bdist, int
         fp->attr_done |= 1u << (e.ctx->device & 31);
       }
       ColPairParams<T> cp;
-      cp.z = wk + cs; cp.out = ac + cs; cp.s = s; cp.bdist = bd;
+      cp.z = wks; cp.out = ac + cs; cp.s = s; cp.bdist = bd; cp.zs = ws; cp.zbdist = wbd;
       cp.R1 = (int)R1; cp.cols = (int)cb; cp.batches = (int)batches; cp.kind = kind; cp.f0 = f0; cp.f = f; cp.dtw = dtw;
       JTB_TRY(fast_stage_table<T>(e, fp->logn, fp->loge, &cp.twg));
       const i64 nblk = (cb / fp->W) * (R1 / 2 + 1) * batches;

@@ -322,6 +322,11 @@ template <typename T> struct RowR2RParams {
   const cx<T>* twg;     // stage twiddles
   const cx<T>* rtw;     // exp(-2 pi i k / n), k <= N/2
   const cx<T>* dtw;     // exp(-i pi k / (2n)), k < n   (DCT/DST)
+  // RK_DHT, last pass of DoubleDHT_2D.forward (W even): the CTA's lines are the row PAIRS (r, pair_rows - r) of one
+  // pair_rows x n array -- lines w = 2j, 2j+1 of a CTA are rows r and R-r; pair 0 is (0, R/2), both self-paired -- and
+  // the epilogue applies yTransform (dht/DoubleDHT_2D.java:1288-1309) before the store:
+  //   H[r][c] = (T[r][c] + T[R-r][c] + T[r][C-c] - T[R-r][C-c]) / 2.   0: plain rows.
+  i64 pair_rows;
 };
 
 template <typename T, int LOGN, int LOGE, int KIND, int W>
@@ -339,8 +344,16 @@ fft_r2r_row_kernel(const RowR2RParams<T> p) {
   const int t = tid % S::TPL, w = tid / S::TPL;
   for (int i = tid; i < FastTw<S>::COUNT_SM; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
   const i64 line0 = (i64)blockIdx.x * W;
-  const bool valid = line0 + w < p.nlines;
-  T* xl = p.a + (valid ? (line0 + w) * p.dist : 0);
+  bool valid = line0 + w < p.nlines;
+  i64 line = line0 + w;
+  bool combine = false;          // paired rows: apply yTransform with the partner line w ^ 1
+  if (KIND == RK_DHT && W >= 2 && p.pair_rows) {
+    const i64 pi = (i64)blockIdx.x * (W / 2) + (w >> 1);
+    valid = pi < p.pair_rows / 2;
+    line = (w & 1) == 0 ? pi : (pi == 0 ? p.pair_rows / 2 : p.pair_rows - pi);
+    combine = pi != 0;
+  }
+  T* xl = p.a + (valid ? line * p.dist : 0);
   C* half = sm + w * N;          // unpadded line buffer for the half-line hand-overs (conflict-free: unit stride)
   C v[S::E];
   // z[j] = v[2j] + i v[2j+1] of the Makhoul-permuted line v[u] = x[2u], v[n-1-u] = x[2u+1] (DST: odd samples negated):
@@ -376,6 +389,57 @@ fft_r2r_row_kernel(const RowR2RParams<T> p) {
 #pragma unroll
   for (int q = H; q < S::E; ++q) half[t + q * S::TPL] = v[q];
   __syncthreads();
+  if (KIND == RK_DHT && W >= 2 && p.pair_rows) {
+    // Row pairs: the outputs of this line stay in registers -- (T[k], T[n-k]) in v[q], (T[N-k], T[N+k]) in v[q+H], both
+    // mirrored column pairs (c, C-c) -- are handed to the partner line through shared memory, combined and stored.
+    const T hf2 = (T)0.5;
+#pragma unroll
+    for (int q = 0; q < H; ++q) {
+      const int k = t + q * S::TPL;
+      if (k == 0) {
+        const C z0 = v[0];
+        const C zm = v[H];
+        v[0] = mk<T>((z0.x + z0.y) * p.f, (z0.x - z0.y) * p.f);        // columns 0 and N: self-mirrored, never combined
+        v[H] = mk<T>((zm.x + zm.y) * p.f, (zm.x - zm.y) * p.f);        // columns N/2 and n - N/2 (V[N/2] = conj Z[N/2])
+      } else {
+        const C a = v[q];
+        const C b = half[N - k];
+        const C wk = __ldg(p.rtw + k);
+        const C ev = mk<T>((a.x + b.x) * hf2, (a.y - b.y) * hf2);
+        const C df = mk<T>((a.x - b.x) * hf2, (a.y + b.y) * hf2);
+        C od = cmul(df, wk);
+        od = mk<T>(od.y, -od.x);
+        const C Vk = cadd(ev, od);
+        const C Vm = mk<T>(ev.x - od.x, -(ev.y - od.y));
+        v[q] = mk<T>((Vk.x - Vk.y) * p.f, (Vk.x + Vk.y) * p.f);          // T[k], T[n-k]
+        v[q + H] = mk<T>((Vm.x - Vm.y) * p.f, (Vm.x + Vm.y) * p.f);      // T[N-k], T[N+k]
+      }
+    }
+    __syncthreads();                                                     // every read of `half` is done
+#pragma unroll
+    for (int q = 0; q < H; ++q) { half[t + q * S::TPL] = v[q]; half[t + (q + H) * S::TPL] = v[q + H]; }
+    __syncthreads();
+    if (!valid) return;
+    const C* other = sm + (w ^ 1) * N;
+#pragma unroll
+    for (int q = 0; q < H; ++q) {
+      const int k = t + q * S::TPL;
+      C o1 = v[q], o2 = v[q + H];
+      if (combine) {
+        const C b1 = other[t + q * S::TPL], b2 = other[t + (q + H) * S::TPL];
+        if (k != 0) o1 = mk<T>((o1.x + b1.x + o1.y - b1.y) * hf2, (o1.y + b1.y + o1.x - b1.x) * hf2);
+        o2 = mk<T>((o2.x + b2.x + o2.y - b2.y) * hf2, (o2.y + b2.y + o2.x - b2.x) * hf2);
+      }
+      if (k == 0) {
+        xl[0] = o1.x; xl[N] = o1.y;
+        xl[N / 2] = o2.x; xl[n - N / 2] = o2.y;
+      } else {
+        xl[k] = o1.x; xl[n - k] = o1.y;
+        xl[N - k] = o2.x; xl[N + k] = o2.y;
+      }
+    }
+    return;
+  }
   if (!valid) return;
   T* out = xl;
   const T hf = (T)0.5;
@@ -436,9 +500,9 @@ fft_r2r_row_kernel(const RowR2RParams<T> p) {
 // k = k1 + R1*k2 finds its partner n-k = (R1-k1) + R1*(R2-1-k2) in the same CTA (through shared memory) and the
 // final real results are stored directly -- no separate sweep for k_r2r_colpost.
 template <typename T> struct ColPairParams {
-  const cx<T>* z;       // first-pass output, rows s apart, batch bdist apart
-  cx<T>* out;
-  i64 s, bdist;
+  const cx<T>* z;       // first-pass output, rows zs apart, batch zbdist apart
+  cx<T>* out;           // rows s apart, batch bdist apart
+  i64 s, bdist, zs, zbdist;
   int R1, cols, batches; // lines per column, complex columns in this launch, arrays
   int kind;
   T f0, f;
@@ -467,10 +531,10 @@ __global__ void __launch_bounds__(2 * W * Sched<LOGN, LOGE>::TPL, 2) fft_colpair
   const int batch = b / pairs;
   const int k1 = u == 0 ? pr : (p.R1 - pr) % p.R1;
   const i64 n = (i64)p.R1 * R2;
-  const C* src = p.z + batch * p.bdist + (i64)k1 * R2 * p.s + cg * W + w;
+  const C* src = p.z + batch * p.zbdist + (i64)k1 * R2 * p.zs + cg * W + w;
   C v[S::E];
 #pragma unroll
-  for (int q = 0; q < S::E; ++q) v[q] = src[(i64)(t + q * S::TPL) * p.s];
+  for (int q = 0; q < S::E; ++q) v[q] = src[(i64)(t + q * S::TPL) * p.zs];
   FastLoop<T, S, 0, true, W2>::run(v, sm, twt, t, wu, p.twg);
   if (S::S > 1) __syncthreads();
 #pragma unroll

@@ -28,6 +28,12 @@ template <typename T> struct MixedParams {
   int swap_in, swap_out, has_scale;
   T scale;
   const cx<T>* wtab;   // exp(-2 pi i j / n), j < n
+  // two-pass transform of a long line N = N1*N2 (mixed_twopass_contig): the first pass multiplies output element i of
+  // line l by the four-step twiddle W_N^(i * (l mod tw_mod)) = twA[m >> tw_logL] * twB[m & (2^tw_logL - 1)]; the second
+  // pass reads contiguous lines but stores with the LINE index fastest (wfast_out: transposed, coalesced store)
+  int tw_mode, tw_mod, tw_logL, wfast_out;
+  const cx<T>* twA;
+  const cx<T>* twB;
 };
 
 __host__ __device__ __forceinline__ unsigned mix_magic(unsigned d) { return d <= 1 ? 0u : (unsigned)(0x100000000ULL / d) + 1u; }
@@ -94,7 +100,8 @@ __device__ __forceinline__ void mixed_stage(const cx<T>* __restrict__ src, cx<T>
   typedef cx<T> C;
   const int nb = n / R;                 // butterflies per line
   const int tstep = n / (Ns * R);       // twiddle index step: W_{Ns R}^{m} = wtab[m * tstep]
-  for (int idx = tid; idx < nb * lines; idx += nthreads) {
+  // line-interleaved tiles decode (b, w) with the full tile width: a partial last tile runs its unused columns too
+  for (int idx = tid; idx < nb * (wfast ? W : lines); idx += nthreads) {
     int b, w;
     if (wfast) { w = idx & (W - 1); b = idx >> logW; } else { w = mix_div(idx, m_nb, nb); b = idx - w * nb; }
     const int k = b - mix_div(b, m_ns, Ns) * Ns;
@@ -122,7 +129,7 @@ template <typename T> __global__ void __launch_bounds__(512, 1) fft_mixed_kernel
   typedef cx<T> C;
   JTB_DYN_SMEM(smem_raw);
   const int n = p.n, W = p.W, wfast = p.wfast;
-  const int ld = n + 1;
+  const int ld = n | 1;            // odd row length: column accesses of the [w][ld] layout are conflict-free
   C* bufA = reinterpret_cast<C*>(smem_raw);
   C* bufB = bufA + (size_t)W * ld;
   const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -157,11 +164,18 @@ template <typename T> __global__ void __launch_bounds__(512, 1) fft_mixed_kernel
     Ns *= R;
     C* t = src; src = dst; dst = t;
   }
+  const bool wf_out = wfast || p.wfast_out;
+  // with the line index fastest (and blockDim a multiple of W) a thread always stores for the same line
+  const int jw = p.tw_mode ? (int)((line0 + (tid & (W - 1))) % p.tw_mod) : 0;
   for (int idx = tid; idx < n * W; idx += nthreads) {
     int i, w;
-    if (wfast) { w = idx & (W - 1); i = idx >> p.logW; } else { w = mix_div(idx, p.m_n, n); i = idx - w * n; }
+    if (wf_out) { w = idx & (W - 1); i = idx >> p.logW; } else { w = mix_div(idx, p.m_n, n); i = idx - w * n; }
     if (w < lines) {
       C z = src[wfast ? i * W + w : w * ld + i];
+      if (p.tw_mode) {
+        const int m = i * jw;        // < N1*N2 <= 2^31 (host check)
+        z = cmul(z, cmul(__ldg(p.twA + (m >> p.tw_logL)), __ldg(p.twB + (m & ((1 << p.tw_logL) - 1)))));
+      }
       if (p.has_scale) { z.x *= p.scale; z.y *= p.scale; }
       if (p.swap_out) z = cswap(z);
       p.out[geo_off(p.go, line0 + w) + (i64)i * p.go.stride] = z;

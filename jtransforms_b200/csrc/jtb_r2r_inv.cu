@@ -286,7 +286,7 @@ int fast_r2r_cols_inv(Engine<T>& e, T* a, i64 n, i64 Cn, i64 batches, i64 bdist,
   JTB_TRY(set_smem_once(f2, e.ctx->device));
   // pass A: rows q = k1 + R1*q2 -> work rows k1*R2 + m2
   ColPairParams<T> cp;
-  cp.z = ac; cp.out = wk; cp.s = s; cp.bdist = bd;
+  cp.z = ac; cp.out = wk; cp.s = s; cp.bdist = bd; cp.zs = s; cp.zbdist = bd;
   cp.R1 = (int)R1; cp.cols = (int)H; cp.batches = (int)batches; cp.kind = kind; cp.f0 = f0; cp.f = f; cp.dtw = dtw;
   JTB_TRY(fast_stage_table<T>(e, f1->logn, f1->loge, &cp.twg));
   const i64 nblk = (H / f1->W) * (R1 / 2 + 1) * batches;

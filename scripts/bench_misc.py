@@ -12,9 +12,12 @@ def timeit(fn, reps=5):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 
-cases = [("1d", (10368,)), ("1d", (75600,)), ("1d", (1562500,)), ("1d", (6250000,)), ("1d", (1 << 22,)), ("1d", (1 << 24,)),
+cases = [("1d", (10368,)), ("1d", (27000,)), ("1d", (75600,)), ("1d", (165375,)), ("1d", (362880,)), ("1d", (1562500,)), ("1d", (3211264,)),
+         ("1d", (6250000,)), ("1d", (1 << 22,)), ("1d", (1 << 24,)),
          ("2d", (1050, 1050)), ("2d", (1960, 1960)), ("2d", (1024, 1024)), ("2d", (8192, 8192)),
          ("3d", (95, 95, 95)), ("3d", (180, 180, 180)), ("3d", (420, 420, 420)), ("3d", (256, 256, 256)), ("3d", (1024, 1024, 1024))]
+if os.environ.get("MISC_1D_ONLY"):
+    cases = [c for c in cases if c[0] == "1d"]
 for kind, dims in cases:
     n = 1
     for d in dims: n *= d

@@ -447,3 +447,22 @@ def test_plan_destroy_releases_tables(jt):
     gc.collect()
     a3 = x.copy(); f2.complexForward(a3)
     assert np.array_equal(a2, a3)
+
+
+@pytest.mark.parametrize("prec", ["Double", "Float"])
+@pytest.mark.parametrize("n", [10368, 27000, 9 * 1024, 3 * 5 * 7 * 11 * 13, 20000])
+def test_fft1d_mixed_two_pass(jt, prec, n):
+    """smooth lengths beyond one CTA: two mixed-radix passes n = N1*N2 with the four-step twiddle fused into the
+    first store and a transposed second store (the reference's FFTPACK sizes, fft/BenchmarkDoubleFFT.java:56)"""
+    pc.fft1d_complex(jt, prec, n)
+
+
+def test_fft1d_mixed_two_pass_batch_and_real(jt):
+    """batched lines (jtb_exec_batch) and the real transforms that sit on top of the complex one"""
+    n = 10368
+    x = o.fill_uniform(2 * n * 3, seed=4, lo=-1.0, hi=1.0)
+    a = x.copy()
+    jt.DoubleFFT_1D(n).complexForwardBatch(a, 3, 2 * n)
+    for b in range(3):
+        assert o.rel_l2(a[2 * n * b:2 * n * (b + 1)], o.complex_forward_1d(x[2 * n * b:2 * n * (b + 1)], n)) < 1e-12 * 14
+    pc.fft1d_real(jt, "Double", 12000)

@@ -119,3 +119,26 @@ def test_plans_on_two_devices_in_one_process():
         b = y.copy()
         jt.DoubleDCT_1D(8192, device=dev).forward(b, True)
         assert o.rel_l2(b, o.dct_forward_nd(y, (8192,), True)) < 1e-12 * 13
+
+
+@pytest.mark.parametrize("prec", ["Float", "Double"])
+def test_batched_bluestein_split_over_devices(prec):
+    """BASELINE config 3 behind the drop-in call: a batch of prime-length transforms on ONE host array, split into
+    contiguous blocks over the plan's devices (jtb_exec_batch on a multi-GPU plan; no collective).  Virtual ranks on a
+    1-GPU box, every GPU otherwise; against the oracle line by line."""
+    import numpy as np
+    import torch
+    import jtransforms_b200 as jt
+    from oracle import jt_oracle as o
+    n, howmany = 10007, 7                         # prime length -> Bluestein; 7 lines over 2..8 devices: ragged blocks
+    ng = torch.cuda.device_count()
+    for devices in ([0, 0, 0], list(range(ng)) if ng > 1 else [0, 0]):
+        dt = np.float32 if prec == "Float" else np.float64
+        x = o.fill_uniform(2 * n * howmany, seed=12, lo=-1.0, hi=1.0).astype(dt)
+        a = x.copy()
+        f = getattr(jt, prec + "FFT_1D")(n, devices=devices)
+        f.complexForwardBatch(a, howmany, 2 * n)
+        tol = (1e-5 if prec == "Float" else 1e-12) * 14
+        for b in range(howmany):
+            want = o.complex_forward_1d(x[2 * n * b:2 * n * (b + 1)].astype(np.float64), n)
+            assert o.rel_l2(a[2 * n * b:2 * n * (b + 1)].astype(np.float64), want) < tol, (devices, b)

@@ -348,3 +348,11 @@ def test_large_64bit_indexing(jt):
     b = x.copy()
     jt.DoubleFFT_1D(n).complexForward(b)
     pc.check(b, o.complex_forward_1d(x, n), "Double", n, "2^26")
+
+
+@pytest.mark.parametrize("prec", ["Double", "Float"])
+@pytest.mark.parametrize("n", [10368, 27000, 75600, 165375, 362880, 1562500, 3211264, 6250000])
+def test_fft1d_smooth_reference_sizes(jt, prec, n):
+    """the reference benchmark's mixed-radix lengths (fft/BenchmarkDoubleFFT.java:56; FFTPACK path
+    fft/DoubleFFT_1D.java:6630-8009): two mixed-radix passes n = N1*N2 here, against the oracle"""
+    pc.fft1d_complex(jt, prec, n)
