@@ -116,6 +116,9 @@ template <typename T> struct Engine {
   typedef cx<T> C;
   Ctx* ctx;
   cudaStream_t st;
+  // > 0: strided lean passes launch at most this many (persistent) CTAs, each walking over several tiles -- lets a pass
+  // share the SMs with a concurrent kernel on another stream instead of flooding every slot (pipelined slab exchange)
+  int cta_limit = 0;
   Engine(Ctx* c, cudaStream_t s) : ctx(c), st(s) {}
   static const char* pname();
   static int max_logn_contig();    // longest line one CTA transforms (contiguous lines)
@@ -148,6 +151,9 @@ template <typename T>
 int fast_scatter(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, int nranks, int rank, void* const* peers,
                  bool inverse, i64 slice_base = -1, bool back = false, i64 col0 = 0, i64 ncols = -1);   // jtb_fast.cu
 template <typename T> int fast_scatter_width(i64 R, i64 Cn);   // jtb_fast.cu
+template <typename T>
+int fast_scatter_tma(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, i64 S, int nranks, int rank, void* const* peers,
+                     bool inverse, i64 col0, i64 ncols, bool* handled);   // jtb_tma.cu
 template <typename T>
 int fast_c2c_out(Engine<T>& e, cx<T>* a, const Geo& g, cx<T>* out, i64 out_dist, i64 out_stride, i64 nlines, int logn,
                  bool inverse, bool has_scale, T scale, bool* handled);   // jtb_fast.cu

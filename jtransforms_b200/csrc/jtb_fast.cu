@@ -162,7 +162,13 @@ int fast_c2c_out(Engine<T>& e, cx<T>* a, const Geo& g, cx<T>* out, i64 out_dist,
     const int pf_default = (sizeof(T) == 8 && bytes_stride <= (64 << 10)) ? 111 : 0;
     p.prefetch = p.reps == 1 ? (epf ? atoi(epf) : pf_default) : 0;
   }
-  const i64 nblk = ((nlines + pick->W - 1) / pick->W + p.reps - 1) / p.reps;
+  i64 nblk = ((nlines + pick->W - 1) / pick->W + p.reps - 1) / p.reps;
+  if (strided && e.cta_limit > 0 && nblk > e.cta_limit) {
+    const i64 ntiles = (nlines + pick->W - 1) / pick->W;
+    p.reps = (int)((ntiles + e.cta_limit - 1) / e.cta_limit);
+    p.prefetch = 0;
+    nblk = (ntiles + p.reps - 1) / p.reps;
+  }
   if (nblk > 0x7fffffffLL) return ST_OK;
   // Measured and removed (profiles/r01_sweep_cluster.log, r01_sweep_raster.log): cluster launch of adjacent column
   // groups, ld.global.L2::256B hints and interleaved CTA rasterisation all slow the strided passes down.
@@ -210,6 +216,15 @@ int fast_scatter(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, int nranks
   if (!is_pow2(R) || nranks < 1 || nranks > 8 || !is_pow2(nranks) || R % nranks) {
     set_error("fused exchange needs power-of-two rows and 1, 2, 4 or 8 ranks");
     return ST_UNSUPPORTED;
+  }
+  {
+    // exchange stores issued by the TMA engine instead of the load/store unit (JTB_SCATTER_TMA=1; jtb_tma.cuh)
+    static const bool tma = getenv("JTB_SCATTER_TMA") && atoi(getenv("JTB_SCATTER_TMA")) != 0;
+    if (tma && !back && slice_base < 0) {
+      bool handled = false;
+      JTB_TRY(fast_scatter_tma<T>(e, a, Ls, R, Cn, Ls * nranks, nranks, rank, peers, inverse, col0, ncols, &handled));
+      if (handled) return ST_OK;
+    }
   }
   const int logn = ilog2(R);
   ScatterEntry<T>* pick = nullptr;

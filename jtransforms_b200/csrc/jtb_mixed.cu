@@ -21,6 +21,23 @@ static bool mixed_factor(i64 n, int* radix, int* nstages) {
   return rem == 1 && ns > 0;
 }
 
+template <typename T> static bool mixed_small_radices(const MixedParams<T>& p) {
+  static const bool off = getenv("JTB_MIXED_NO_BIG") != nullptr;
+  if (off) return false;
+  for (int s = 0; s < p.nstages; ++s) if (p.radix[s] > 5) return false;
+  return true;
+}
+template <typename T> static int mixed_attr(Engine<T>& e) {
+  static bool attr_done[16] = {false, false};
+  const int dv = (e.ctx->device & 7) * 2 + (sizeof(T) == 8 ? 0 : 1);
+  if (!attr_done[dv]) {
+    JTB_CUDA(cudaFuncSetAttribute((fft_mixed_kernel<T, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024));
+    JTB_CUDA(cudaFuncSetAttribute((fft_mixed_kernel<T, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024));
+    attr_done[dv] = true;
+  }
+  return ST_OK;
+}
+
 template <typename T>
 int mixed_c2c(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, i64 n, bool inverse, bool has_scale, T scale, bool* handled) {
   typedef cx<T> C;
@@ -46,12 +63,7 @@ int mixed_c2c(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, i64 n, bool inve
   while (W > 1 && (size_t)W * line_bytes > cap) W >>= 1;
   if ((i64)W > nlines) W = (int)nlines;
   const size_t smem = (size_t)W * line_bytes;
-  static bool attr_done[16] = {false, false};
-  const int dv = (e.ctx->device & 7) * 2 + (sizeof(T) == 8 ? 0 : 1);
-  if (!attr_done[dv]) {
-    JTB_CUDA(cudaFuncSetAttribute(fft_mixed_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap + 1024));
-    attr_done[dv] = true;
-  }
+  JTB_TRY(mixed_attr<T>(e));
   const std::string key = mkkey("mixw", e.pname(), n);
   void* d = e.ctx->table(key);
   if (!d) {
@@ -76,10 +88,12 @@ int mixed_c2c(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, i64 n, bool inve
     }
   }
   const i64 work = (i64)W * n / 4;                       // butterflies of a radix-4 stage
-  const unsigned threads = work >= 512 ? 512u : (work >= 256 ? 256u : (work >= 128 ? 128u : 64u));
+  const bool big = mixed_small_radices(p) && work >= 1024;
+  const unsigned threads = big ? 1024u : (work >= 512 ? 512u : (work >= 256 ? 256u : (work >= 128 ? 128u : 64u)));
   const i64 nblk = (nlines + W - 1) / W;
   if (nblk > 0x7fffffffLL) return ST_OK;
-  JTB_LAUNCH(fft_mixed_kernel<T>, (unsigned)nblk, threads, smem, e.st, p);
+  if (big) JTB_LAUNCH((fft_mixed_kernel<T, true>), (unsigned)nblk, threads, smem, e.st, p);
+  else JTB_LAUNCH((fft_mixed_kernel<T, false>), (unsigned)nblk, threads, smem, e.st, p);
   JTB_CUDA(cudaGetLastError());
   e.ctx->launches++;
   *handled = true;
@@ -119,17 +133,14 @@ template <typename T> int mixed_setup(Engine<T>& e, MixedParams<T>& p, i64 n, in
 template <typename T> int mixed_launch(Engine<T>& e, MixedParams<T>& p) {
   typedef cx<T> C;
   const size_t smem = (size_t)p.W * 2 * (size_t)(p.n + 1) * sizeof(C);
-  static bool attr_done[16] = {false, false};
-  const int dv = (e.ctx->device & 7) * 2 + (sizeof(T) == 8 ? 0 : 1);
-  if (!attr_done[dv]) {
-    JTB_CUDA(cudaFuncSetAttribute(fft_mixed_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024));
-    attr_done[dv] = true;
-  }
+  JTB_TRY(mixed_attr<T>(e));
   const i64 work = (i64)p.W * p.n / 4;
-  const unsigned threads = work >= 512 ? 512u : (work >= 256 ? 256u : (work >= 128 ? 128u : 64u));
+  const bool big = mixed_small_radices(p) && work >= 1024;
+  const unsigned threads = big ? 1024u : (work >= 512 ? 512u : (work >= 256 ? 256u : (work >= 128 ? 128u : 64u)));
   const i64 nblk = (p.nlines - p.line_base + p.W - 1) / p.W;
   if (nblk > 0x7fffffffLL) { set_error("too many lines"); return ST_UNSUPPORTED; }
-  JTB_LAUNCH(fft_mixed_kernel<T>, (unsigned)nblk, threads, smem, e.st, p);
+  if (big) JTB_LAUNCH((fft_mixed_kernel<T, true>), (unsigned)nblk, threads, smem, e.st, p);
+  else JTB_LAUNCH((fft_mixed_kernel<T, false>), (unsigned)nblk, threads, smem, e.st, p);
   JTB_CUDA(cudaGetLastError());
   e.ctx->launches++;
   return ST_OK;

@@ -125,7 +125,10 @@ __device__ __forceinline__ void mixed_stage(const cx<T>* __restrict__ src, cx<T>
   }
 }
 
-template <typename T> __global__ void __launch_bounds__(512, 1) fft_mixed_kernel(const MixedParams<T> p) {
+// BIG: 1024-thread CTAs (64 registers) for plans whose radices are all <= 5 -- twice the warps to hide the shared-memory
+// and twiddle latency of the stage loops; the generic odd radices (7, 11, 13) keep the 512-thread build.
+template <typename T, bool BIG>
+__global__ void __launch_bounds__(BIG ? 1024 : 512, 1) fft_mixed_kernel(const MixedParams<T> p) {
   typedef cx<T> C;
   JTB_DYN_SMEM(smem_raw);
   const int n = p.n, W = p.W, wfast = p.wfast;
@@ -156,9 +159,9 @@ template <typename T> __global__ void __launch_bounds__(512, 1) fft_mixed_kernel
       case 3: mixed_stage<T, 3>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W, p.logW, p.m_nb[s], p.m_ns[s]); break;
       case 4: mixed_stage<T, 4>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W, p.logW, p.m_nb[s], p.m_ns[s]); break;
       case 5: mixed_stage<T, 5>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W, p.logW, p.m_nb[s], p.m_ns[s]); break;
-      case 7: mixed_stage<T, 7>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W, p.logW, p.m_nb[s], p.m_ns[s]); break;
-      case 11: mixed_stage<T, 11>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W, p.logW, p.m_nb[s], p.m_ns[s]); break;
-      default: mixed_stage<T, 13>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W, p.logW, p.m_nb[s], p.m_ns[s]); break;
+      case 7: if (!BIG) mixed_stage<T, 7>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W, p.logW, p.m_nb[s], p.m_ns[s]); break;
+      case 11: if (!BIG) mixed_stage<T, 11>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W, p.logW, p.m_nb[s], p.m_ns[s]); break;
+      default: if (!BIG) mixed_stage<T, 13>(src, dst, n, Ns, lines, ld, p.wtab, tid, nthreads, wfast, W, p.logW, p.m_nb[s], p.m_ns[s]); break;
     }
     __syncthreads();
     Ns *= R;

@@ -321,6 +321,12 @@ template <typename T> int slab_pipe_produce(jtb_slab* m, cx<T>* a, bool inverse,
 // consumer side on `st2`: block j of the re-slabbed array [S][Rh][C] once every peer has announced it; `st` joins at the end
 template <typename T> int slab_pipe_consume(jtb_slab* m, bool inverse, bool scale, cudaStream_t st, int buf, int nb) {
   Engine<T> e2(m->ctx, m->st2);
+  {
+    // the slice-axis pass shares the SMs with the exchange kernel of the next block: a bounded number of persistent CTAs
+    // (JTB_PIPE_K1_CTAS, 0 = unbounded) so that it takes a fixed share of the slots instead of all of them
+    static const char* ek = getenv("JTB_PIPE_K1_CTAS");
+    e2.cta_limit = ek ? atoi(ek) : 148;
+  }
   const i64 S = m->S, Rh = m->Rh, Cn = m->Cn, cc = Cn / nb;
   const T sc = (T)(1.0 / ((double)S * (double)m->R * (double)Cn));
   for (int j = 0; j < nb; ++j) {

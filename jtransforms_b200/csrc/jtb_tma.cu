@@ -1,5 +1,6 @@
 // Host dispatch of fft_tma_kernel (jtb_tma.cuh): tensor-map construction and the variant registry.
 #include <cstdlib>
+#include <cstring>
 
 #include "jtb_engine_impl.cuh"
 #include "jtb_tma.cuh"
@@ -138,7 +139,96 @@ int fast_tma_c2c(Engine<T>& e, cx<T>* a, const Geo& g, i64 nlines, int logn, boo
   *handled = true;
   return ST_OK;
 }
+// ------------------------------------------------------------------------------------------ fused k2 + exchange, TMA stores
+namespace {
+template <typename T> struct ScatterTmaEntry {
+  int logn, W, threads, smem, loge;
+  void (*kern)(const PeerMaps, const ScatterParams<T>);
+  unsigned attr_done;
+};
+template <typename T, int LOGN, int LOGE, int W> ScatterTmaEntry<T> make_scatter_tma() {
+  typedef Sched<LOGN, LOGE> S;
+  ScatterTmaEntry<T> e;
+  e.logn = LOGN; e.loge = LOGE; e.W = W; e.threads = W * S::TPL;
+  e.smem = (int)((FastAddr<T, S, true, W>::TILE + FastTw<S>::COUNT_SM) * sizeof(cx<T>)) + 128;
+  e.kern = fft_scatter_tma_kernel<T, LOGN, LOGE, W>;
+  e.attr_done = 0;
+  return e;
+}
+template <typename T> std::vector<ScatterTmaEntry<T>>& scatter_tma_registry();
+template <> std::vector<ScatterTmaEntry<double>>& scatter_tma_registry<double>() {
+  static std::vector<ScatterTmaEntry<double>> r = {make_scatter_tma<double, 9, 3, 8>(), make_scatter_tma<double, 8, 4, 8>(),
+                                                   make_scatter_tma<double, 10, 4, 8>()};
+  return r;
+}
+template <> std::vector<ScatterTmaEntry<float>>& scatter_tma_registry<float>() {
+  static std::vector<ScatterTmaEntry<float>> r = {make_scatter_tma<float, 9, 3, 16>(), make_scatter_tma<float, 10, 4, 16>()};
+  return r;
+}
+}  // namespace
+
+// forward re-slabbing only (the inverse exchange interleaves rows of different sources: no rectangular box per peer)
+template <typename T>
+int fast_scatter_tma(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, i64 S, int nranks, int rank, void* const* peers,
+                     bool inverse, i64 col0, i64 ncols, bool* handled) {
+  *handled = false;
+  if (!is_pow2(R) || nranks < 2 || nranks > 8 || !is_pow2(nranks) || R % nranks) return ST_OK;
+  const i64 Rh = R / nranks;
+  if (Rh > 256 || S * Rh > 0x7fffffffLL) return ST_OK;   // box dimension limit
+  const int logn = ilog2(R);
+  ScatterTmaEntry<T>* pick = nullptr;
+  for (auto& f : scatter_tma_registry<T>())
+    if (f.logn == logn && Cn % f.W == 0) { pick = &f; break; }
+  if (!pick) return ST_OK;
+  if (ncols < 0) { col0 = 0; ncols = Cn; }
+  if (col0 < 0 || col0 % pick->W || ncols % pick->W || col0 + ncols > Cn || ncols == 0) return ST_OK;
+  if ((Cn * (i64)sizeof(cx<T>)) % 16) return ST_OK;
+  encode_fn enc = get_encoder();
+  if (!enc) return ST_OK;
+  PeerMaps maps;
+  memset(&maps, 0, sizeof maps);
+  for (int h = 0; h < nranks; ++h) {
+    if (((uintptr_t)peers[h]) % 16) return ST_OK;
+    const cuuint64_t dims[2] = {(cuuint64_t)(2 * Cn), (cuuint64_t)(S * Rh)};
+    const cuuint64_t strides[1] = {(cuuint64_t)(Cn * (i64)sizeof(cx<T>))};
+    const cuuint32_t box[2] = {(cuuint32_t)(2 * pick->W), (cuuint32_t)Rh};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = enc(&maps.m[h], sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, peers[h],
+                            dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return ST_OK;
+  }
+  const int dv = e.ctx->device & 31;
+  if (!(pick->attr_done & (1u << dv))) {
+    JTB_CUDA(cudaFuncSetAttribute(pick->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pick->smem));
+    pick->attr_done |= 1u << dv;
+  }
+  ScatterParams<T> p;
+  memset(&p, 0, sizeof p);
+  p.a = a;
+  p.Ls = (int)Ls; p.C = (int)Cn; p.logRh = ilog2(Rh); p.slice0 = (int)(rank * Ls); p.inverse = inverse;
+  p.row_base = (long long)p.slice0 * Rh; p.row_ls_mul = (int)Rh; p.row_mul = 1;
+  p.col0 = (int)col0; p.groups = (int)(ncols / pick->W);
+  JTB_TRY(fast_stage_table<T>(e, logn, pick->loge, &p.twg));
+  const i64 nblk = Ls * (ncols / pick->W);
+  if (nblk > 0x7fffffffLL) return ST_OK;
+  JTB_LAUNCH(pick->kern, (unsigned)nblk, (unsigned)pick->threads, (size_t)pick->smem, e.st, maps, p);
+  JTB_CUDA(cudaGetLastError());
+  e.ctx->launches++;
+  *handled = true;
+  return ST_OK;
+}
 #endif
+
+#ifdef JTB_EMU
+template <typename T>
+int fast_scatter_tma(Engine<T>&, const cx<T>*, i64, i64, i64, i64, int, int, void* const*, bool, i64, i64, bool* handled) {
+  *handled = false;
+  return ST_OK;
+}
+#endif
+template int fast_scatter_tma<double>(Engine<double>&, const double2*, i64, i64, i64, i64, int, int, void* const*, bool, i64, i64, bool*);
+template int fast_scatter_tma<float>(Engine<float>&, const float2*, i64, i64, i64, i64, int, int, void* const*, bool, i64, i64, bool*);
 
 template int fast_tma_c2c<double>(Engine<double>&, double2*, const Geo&, i64, int, bool, bool, double, bool*);
 template int fast_tma_c2c<float>(Engine<float>&, float2*, const Geo&, i64, int, bool, bool, float, bool*);

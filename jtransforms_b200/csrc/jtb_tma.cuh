@@ -77,6 +77,12 @@ template <int N> __device__ __forceinline__ void tma_store_wait() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+__device__ __forceinline__ void tma_store_2d(const void* src, const CUtensorMap* map, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(x), "r"(y)
+               : "memory");
+}
+
 // rows per TMA box (box dimensions are limited to 256)
 template <int N> struct TmaBox { static constexpr int ROWS = N > 256 ? 256 : N; };
 
@@ -172,6 +178,58 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaParams<T> p) {
     }
   }
   if (OUT == 1 && gt == 0) tma_store_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k2 pass of the slab-decomposed 3-D transform with the all-to-all carried by the TMA engine: same transform as
+// fft_scatter_kernel (jtb_fast.cuh), but the finished tile goes back into shared memory and leaves as ONE bulk tensor
+// store per destination GPU (rows [h*Rh, (h+1)*Rh) of the tile = an Rh x 128-byte box of peer h's receive buffer)
+// instead of 16-byte LSU stores from every thread -- the SM's load/store unit no longer carries the NVLink traffic.
+// maps.m[h]: rank-2 tensor map of peer h's [S*Rh rows][C columns] receive buffer (peer-mapped memory).
+struct PeerMaps { CUtensorMap m[8]; };
+
+template <typename T, int LOGN, int LOGE, int W>
+__global__ void __launch_bounds__(W * Sched<LOGN, LOGE>::TPL, (Sched<LOGN, LOGE>::E <= 8 ? FastOcc<W * Sched<LOGN, LOGE>::TPL>::MINB
+                                                                                      : (FastOcc<W * Sched<LOGN, LOGE>::TPL>::MINB + 1) / 2))
+fft_scatter_tma_kernel(const __grid_constant__ PeerMaps maps, const ScatterParams<T> p) {
+  typedef Sched<LOGN, LOGE> S;
+  typedef cx<T> C;
+  typedef FastAddr<T, S, true, W> A;
+  static_assert(!A::ROWPAD, "TMA tiles are dense [row][W]");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  C* sm = reinterpret_cast<C*>(smem_raw);
+  C* twt = sm + A::TILE;
+  const int tid = threadIdx.x;
+  const int w = tid % W, t = tid / W;
+  for (int i = tid; i < FastTw<S>::COUNT_SM; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
+  const int groups = p.groups;
+  const int ls = blockIdx.x / groups;
+  const int c0 = p.col0 + (blockIdx.x - ls * groups) * W;
+  const C* src = p.a + (i64)ls * S::N * p.C + c0 + w;
+  C v[S::E];
+#pragma unroll
+  for (int q = 0; q < S::E; ++q) v[q] = src[(i64)(t + q * S::TPL) * p.C];
+  if (p.inverse) {
+#pragma unroll
+    for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
+  }
+  FastLoop<T, S, 0, true, W>::run(v, sm, twt, t, w, p.twg);
+  if (p.inverse) {
+#pragma unroll
+    for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
+  }
+  if (S::S > 1) __syncthreads();                     // the last gather of every thread is done
+#pragma unroll
+  for (int q = 0; q < S::E; ++q) sm[A::at(t + q * S::TPL, w)] = v[q];
+  fence_proxy_async();
+  __syncthreads();
+  if (tid == 0) {
+    const int Rh = 1 << p.logRh, P = S::N >> p.logRh;
+    const int row0 = (int)(p.row_base + (long long)ls * p.row_ls_mul);
+    for (int h = 0; h < P; ++h) tma_store_2d(sm + (size_t)h * Rh * W, &maps.m[h], 2 * c0, row0);
+    tma_store_commit();
+    tma_store_wait_read<0>();                        // the tile has been read; the writes complete with the kernel
+  }
 }
 
 }  // namespace jtb
