@@ -46,6 +46,7 @@ template <typename T> struct Fast2Params {
   const cx<T>* bigA;
   const cx<T>* bigB;
   int big_logL;
+  int prefetch;       // FM_RFFT: prefetch.global.L2 of the lines `prefetch` CTAs ahead (0 = off)
 };
 
 // PRE_UNPERM_* (second pass of a long strided inverse DCT/DST column, jtb_r2r_inv.cuh) act on the STORE: output
@@ -78,6 +79,15 @@ fft_fast2_kernel(const Fast2Params<T> p) {
   const int c = (int)(line - g * p.c0);
   const i64 g_hi = g / p.gmod;
   const int g_lo = (int)(g - g_hi * p.gmod);
+#ifndef JTB_EMU
+  if (MODE == FM_RFFT && p.prefetch > 0) {
+    const i64 pl = line0 + (i64)p.prefetch * W + w;
+    if (pl < p.nlines) {
+      const char* pb = reinterpret_cast<const char*>(p.in + pl * p.in_gdist);
+      for (int i = t * 128; i < (int)(S::N * sizeof(C)); i += S::TPL * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + i));
+    }
+  }
+#endif
   C v[S::E];
   if (valid && PRE == PRE_CHIRP) {
     const C* src = p.in + g_lo * p.in_gdist + g_hi * p.in_gdist2;
@@ -327,6 +337,7 @@ template <typename T> struct RowR2RParams {
   // the epilogue applies yTransform (dht/DoubleDHT_2D.java:1288-1309) before the store:
   //   H[r][c] = (T[r][c] + T[R-r][c] + T[r][C-c] - T[R-r][C-c]) / 2.   0: plain rows.
   i64 pair_rows;
+  int prefetch;         // > 0: prefetch.global.L2 of the lines the CTA `prefetch` blocks ahead will load (plain rows only)
 };
 
 template <typename T, int LOGN, int LOGE, int KIND, int W>
@@ -354,6 +365,16 @@ fft_r2r_row_kernel(const RowR2RParams<T> p) {
     combine = pi != 0;
   }
   T* xl = p.a + (valid ? line * p.dist : 0);
+#ifndef JTB_EMU
+  if (p.prefetch > 0 && !p.pair_rows) {
+    // pull the lines of a later CTA into L2 while this one computes: n reals = n*sizeof(T)/128 cache lines per line
+    const i64 pl = line0 + (i64)p.prefetch * W + w;
+    if (pl < p.nlines) {
+      const char* pb = reinterpret_cast<const char*>(p.a + pl * p.dist);
+      for (int i = t * 128; i < (int)(n * sizeof(T)); i += S::TPL * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + i));
+    }
+  }
+#endif
   C* half = sm + w * N;          // unpadded line buffer for the half-line hand-overs (conflict-free: unit stride)
   C v[S::E];
   // z[j] = v[2j] + i v[2j+1] of the Makhoul-permuted line v[u] = x[2u], v[n-1-u] = x[2u+1] (DST: odd samples negated):

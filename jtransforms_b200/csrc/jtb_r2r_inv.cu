@@ -182,7 +182,7 @@ int fast_r2r_rows_inv(Engine<T>& e, T* a, i64 dist, i64 nlines, i64 n, int kind,
   if (!r) return ST_OK;
   JTB_TRY(set_smem_once(r, e.ctx->device));
   RowR2RParams<T> p;
-  p.a = a; p.nlines = nlines; p.dist = dist; p.f0 = f0; p.f = f;
+  p.a = a; p.nlines = nlines; p.dist = dist; p.f0 = f0; p.f = f; p.pair_rows = 0; p.prefetch = 0;
   JTB_TRY(fast_stage_table<T>(e, logN, r->loge, &p.twg));
   const cx<T>* tw[JTB_MAX_STAGES];
   JTB_TRY(e.tile_tables(logN, tw, &p.rtw));
