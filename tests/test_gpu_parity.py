@@ -356,3 +356,37 @@ def test_fft1d_smooth_reference_sizes(jt, prec, n):
     """the reference benchmark's mixed-radix lengths (fft/BenchmarkDoubleFFT.java:56; FFTPACK path
     fft/DoubleFFT_1D.java:6630-8009): two mixed-radix passes n = N1*N2 here, against the oracle"""
     pc.fft1d_complex(jt, prec, n)
+
+
+def test_host_array_beyond_2p31_elements(jt):
+    """SURVEY 8(f) rank 4, the LargeArray range at the boundary: ONE host array of 2^32 floats (16 GiB, more elements
+    than a Java array or a 32-bit index can hold -- what DoubleLargeArray / FloatLargeArray exist for,
+    fft/DoubleFFT_2D.java:230) through jtb_exec: FloatFFT_2D 32768 x 65536 complexForward of two impulses, checked
+    against the closed form at 200 000 sampled bins, at both ends of the array, and through Parseval."""
+    import psutil
+    if psutil.virtual_memory().available < (40 << 30):
+        pytest.skip("needs 40 GiB of free host memory")
+    R, C = 32768, 65536
+    a = np.zeros(2 * R * C, dtype=np.float32)
+    assert a.size == 1 << 32
+    imp = [(5, 7, 1.5, -0.25), (R - 3, C - 11, -0.75, 2.0)]          # (row, column, re, im)
+    for r0, c0, re, im in imp:
+        a[2 * (r0 * C + c0)] = re
+        a[2 * (r0 * C + c0) + 1] = im
+    jt.FloatFFT_2D(R, C).complexForward(a)
+    z = a.view(np.complex64)
+    rng = np.random.default_rng(5)
+    k1 = np.concatenate([rng.integers(0, R, 200000), [0, 0, R - 1, R - 1]])
+    k2 = np.concatenate([rng.integers(0, C, 200000), [0, C - 1, 0, C - 1]])
+    want = np.zeros(k1.size, dtype=np.complex128)
+    for r0, c0, re, im in imp:
+        want += (re + 1j * im) * np.exp(-2j * np.pi * ((k1 * r0) % R / R + (k2 * c0) % C / C))
+    got = z[k1.astype(np.int64) * C + k2].astype(np.complex128)
+    err = np.linalg.norm(got - want) / np.linalg.norm(want)
+    assert err < 1e-5 * 31, err
+    energy = 0.0
+    for blk in np.array_split(np.arange(R), 64):                        # Parseval without a 16 GiB temporary
+        v = a[2 * blk[0] * C:2 * (blk[-1] + 1) * C]
+        energy += float(np.sum(np.square(v.astype(np.float64))))       # FP64 accumulation (a float32 dot loses 1e-3 here)
+    expect = float(R) * C * sum(re * re + im * im for _, _, re, im in imp)
+    assert abs(energy - expect) / expect < 1e-4, (energy, expect)
