@@ -56,8 +56,9 @@ template <typename T> std::vector<TmaEntry<T>>& tma_registry();
 template <> std::vector<TmaEntry<double>>& tma_registry<double>() {
   static std::vector<TmaEntry<double>> r = {
       // first entry of a length is the default; JTB_TMA_NG / JTB_TMA_NST / JTB_TMA_OUT select the others
-      make_tma<double, 9, 3, 8, 2, 3, 0>(), make_tma<double, 9, 3, 8, 1, 3, 0>(), make_tma<double, 9, 3, 8, 1, 3, 1>(),
-      make_tma<double, 9, 3, 8, 2, 3, 1>(), make_tma<double, 9, 3, 8, 1, 2, 0>(), make_tma<double, 9, 3, 8, 2, 2, 0>(),
+      // (two compute groups over a three-stage ring faulted on the B200 -- profiles/r02_ab_tma.log -- and were removed)
+      make_tma<double, 9, 3, 8, 2, 2, 0>(), make_tma<double, 9, 3, 8, 1, 3, 0>(), make_tma<double, 9, 3, 8, 1, 3, 1>(),
+      make_tma<double, 9, 3, 8, 1, 2, 0>(),
   };
   return r;
 }
