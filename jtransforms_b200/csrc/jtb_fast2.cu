@@ -637,8 +637,10 @@ template <> BlueReg<double>& bluereg<double>() {
 }
 template <> BlueReg<float>& bluereg<float>() {
   static BlueReg<float> r = {
-      {mk2x<float, 9, 3, 8, FM_TWID, PRE_CHIRP>(), mk2x<float, 10, 4, 16, FM_TWID, PRE_CHIRP>()},
-      {mk2x<float, 9, 3, 8, FM_CHIRP_OUT, PRE_NONE>(), mk2x<float, 10, 4, 16, FM_CHIRP_OUT, PRE_NONE>()},
+      {mk2x<float, 9, 3, 8, FM_TWID, PRE_CHIRP>(), mk2x<float, 10, 4, 16, FM_TWID, PRE_CHIRP>(),
+       mk2x<float, 10, 4, 8, FM_TWID, PRE_CHIRP>(), mk2x<float, 10, 3, 8, FM_TWID, PRE_CHIRP>()},
+      {mk2x<float, 9, 3, 8, FM_CHIRP_OUT, PRE_NONE>(), mk2x<float, 10, 4, 16, FM_CHIRP_OUT, PRE_NONE>(),
+       mk2x<float, 10, 4, 8, FM_CHIRP_OUT, PRE_NONE>(), mk2x<float, 10, 3, 8, FM_CHIRP_OUT, PRE_NONE>()},
       {mkconv<float, 10, 3, 4>(), mkconv<float, 11, 3, 2>(), mkconv<float, 12, 3, 1>(), mkconv<float, 11, 4, 2>(),
        mkconv<float, 12, 4, 1>()}};
   return r;
