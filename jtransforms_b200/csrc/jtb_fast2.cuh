@@ -88,6 +88,14 @@ fft_fast2_kernel(const Fast2Params<T> p) {
     }
   }
 #endif
+  // four-step twiddle of this thread's outputs: W^(idx*t) and the chain step W^(idx*TPL).  Fetched before the data so that
+  // the two dependent table reads are in flight under the line loads instead of after the last butterfly.
+  C ftw = mk<T>(1, 0), fws = mk<T>(1, 0);
+  if (MODE == FM_TWID) {
+    const int idx = p.tw_src ? g_lo : c;
+    ftw = fs_tw2(p, idx * t);
+    fws = fs_tw2(p, idx * S::TPL);
+  }
   C v[S::E];
   if (valid && PRE == PRE_CHIRP) {
     const C* src = p.in + g_lo * p.in_gdist + g_hi * p.in_gdist2;
@@ -153,9 +161,8 @@ fft_fast2_kernel(const Fast2Params<T> p) {
 
   if (MODE == FM_PLAIN || MODE == FM_TWID) {
     if (MODE == FM_TWID) {
-      const int idx = p.tw_src ? g_lo : c;
-      C tw = fs_tw2(p, idx * t);
-      const C ws = fs_tw2(p, idx * S::TPL);
+      C tw = ftw;
+      const C ws = fws;
 #pragma unroll
       for (int q = 0; q < S::E; ++q) {
         v[q] = cmul(v[q], tw);
