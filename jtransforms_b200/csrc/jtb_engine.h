@@ -151,6 +151,11 @@ template <typename T>
 int fast_scatter(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, int nranks, int rank, void* const* peers,
                  bool inverse, i64 slice_base = -1, bool back = false, i64 col0 = 0, i64 ncols = -1);   // jtb_fast.cu
 template <typename T> int fast_scatter_width(i64 R, i64 Cn);   // jtb_fast.cu
+template <typename T> bool fast_pipe_has(i64 R, i64 S, i64 Cn, int nranks, int nb);   // jtb_fast.cu
+template <typename T>
+int fast_pipe_exchange(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, int nranks, int rank, void* const* peers,
+                       void* const* flag_ptrs, long long epoch, int* counters, int nb, bool inverse, bool has_scale, T scale,
+                       bool* handled);   // jtb_fast.cu
 template <typename T>
 int fast_scatter_tma(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, i64 S, int nranks, int rank, void* const* peers,
                      bool inverse, i64 col0, i64 ncols, bool* handled);   // jtb_tma.cu

@@ -334,6 +334,102 @@ int fast_slice2d(Engine<T>& e, cx<T>* a, i64 nslices, i64 N, bool inverse, bool 
 template int fast_slice2d<double>(Engine<double>&, double2*, i64, i64, bool, bool, double, int, int, void* const*, bool*);
 template int fast_slice2d<float>(Engine<float>&, float2*, i64, i64, bool, bool, float, int, int, void* const*, bool*);
 
+// ------------------------------------------------------------------------------------------ fused exchange + k1 pipeline
+namespace {
+template <typename T> struct PipeEntry {
+  int logn, W, threads, smem, loge;
+  void (*kern)(const PipeParams<T>);
+  unsigned attr_done;
+  int occ[32];
+};
+template <typename T, int LOGN, int LOGE, int W> PipeEntry<T> make_pipe() {
+  typedef Sched<LOGN, LOGE> S;
+  PipeEntry<T> e;
+  e.logn = LOGN; e.loge = LOGE; e.W = W; e.threads = W * S::TPL;
+  e.smem = (int)((FastAddr<T, S, true, W>::TILE + FastTw<S>::COUNT_SM) * sizeof(cx<T>));
+  e.kern = fft_pipe_kernel<T, LOGN, LOGE, W>;
+  e.attr_done = 0;
+  for (int d = 0; d < 32; ++d) e.occ[d] = 0;
+  return e;
+}
+template <typename T> std::vector<PipeEntry<T>>& pipe_registry();
+template <> std::vector<PipeEntry<double>>& pipe_registry<double>() {
+  static std::vector<PipeEntry<double>> r = {make_pipe<double, 9, 3, 8>(), make_pipe<double, 6, 3, 8>(), make_pipe<double, 8, 4, 8>(),
+                                             make_pipe<double, 10, 4, 8>()};
+  return r;
+}
+template <> std::vector<PipeEntry<float>>& pipe_registry<float>() {
+  static std::vector<PipeEntry<float>> r = {make_pipe<float, 9, 3, 16>(), make_pipe<float, 6, 3, 16>()};
+  return r;
+}
+}  // namespace
+
+template <typename T> bool fast_pipe_has(i64 R, i64 S, i64 Cn, int nranks, int nb) {
+#ifdef JTB_EMU
+  (void)R; (void)S; (void)Cn; (void)nranks; (void)nb;
+  return false;
+#else
+  if (R != S || !is_pow2(R) || nranks < 2 || nranks > 8 || !is_pow2(nranks) || nb < 1 || nb > 16) return false;
+  for (auto& f : pipe_registry<T>())
+    if (f.logn == ilog2(R) && Cn % (f.W * nb) == 0) return true;
+  return false;
+#endif
+}
+template bool fast_pipe_has<double>(i64, i64, i64, int, int);
+template bool fast_pipe_has<float>(i64, i64, i64, int, int);
+
+// One launch: exchange (k2 pass, peer stores) of `nb` column blocks interleaved with the slice-axis pass of the blocks
+// that have arrived (fft_pipe_kernel).  Needs R == S (one line length), power-of-two rank counts, zeroed counters
+// (1 + nb ints) and flag arrays of 8 x 16 int64 per rank.  *handled = false when the shape has no variant.
+template <typename T>
+int fast_pipe_exchange(Engine<T>& e, const cx<T>* a, i64 Ls, i64 R, i64 Cn, int nranks, int rank, void* const* peers,
+                       void* const* flag_ptrs, long long epoch, int* counters, int nb, bool inverse, bool has_scale, T scale,
+                       bool* handled) {
+  *handled = false;
+#ifndef JTB_EMU
+  if (!is_pow2(R) || nranks < 2 || nranks > 8 || !is_pow2(nranks) || R % nranks || Ls * nranks != R || nb < 1 || nb > 16) return ST_OK;
+  const int logn = ilog2(R);
+  PipeEntry<T>* pick = nullptr;
+  for (auto& f : pipe_registry<T>())
+    if (f.logn == logn && Cn % (f.W * nb) == 0) { pick = &f; break; }
+  if (!pick) return ST_OK;
+  const i64 gpb = Cn / nb / pick->W;
+  if (2 * (i64)nb * Ls * gpb > 0x7fffffffLL || Ls * R * Cn >= (1LL << 40)) return ST_OK;
+  const int dv = e.ctx->device & 31;
+  if (!(pick->attr_done & (1u << dv))) {
+    JTB_CUDA(cudaFuncSetAttribute(pick->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pick->smem));
+    int sms = 0;
+    JTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pick->occ[dv], pick->kern, pick->threads, pick->smem));
+    JTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e.ctx->device));
+    pick->occ[dv] *= sms;
+    pick->attr_done |= 1u << dv;
+  }
+  if (pick->occ[dv] < 1) return ST_OK;
+  PipeParams<T> p;
+  memset(&p, 0, sizeof p);
+  p.a = a;
+  for (int h = 0; h < 8; ++h) { p.peer[h] = h < nranks ? (cx<T>*)peers[h] : nullptr; p.flags[h] = h < nranks ? (long long*)flag_ptrs[h] : nullptr; }
+  p.recv = (cx<T>*)peers[rank];
+  p.counters = counters;
+  JTB_TRY(e.ctx->ensure_watchdog());
+  p.err = e.ctx->wd_dev;
+  JTB_TRY(fast_stage_table<T>(e, logn, pick->loge, &p.twg));
+  p.epoch = epoch;
+  p.Ls = (int)Ls; p.C = (int)Cn; p.logRh = ilog2(R / nranks); p.P = nranks; p.rank = rank; p.nb = nb; p.gpb = (int)gpb;
+  p.inverse = inverse; p.has_scale = has_scale; p.scale = scale;
+  i64 grid = pick->occ[dv];
+  const i64 total = 2 * (i64)nb * Ls * gpb;
+  if (grid > total) grid = total;
+  JTB_LAUNCH(pick->kern, (unsigned)grid, (unsigned)pick->threads, (size_t)pick->smem, e.st, p);
+  JTB_CUDA(cudaGetLastError());
+  e.ctx->launches++;
+  *handled = true;
+#endif
+  return ST_OK;
+}
+template int fast_pipe_exchange<double>(Engine<double>&, const double2*, i64, i64, i64, int, int, void* const*, void* const*, long long, int*, int, bool, bool, double, bool*);
+template int fast_pipe_exchange<float>(Engine<float>&, const float2*, i64, i64, i64, int, int, void* const*, void* const*, long long, int*, int, bool, bool, float, bool*);
+
 // smallest column window granularity the fused exchange supports for R-point columns (0: no fused kernel)
 template <typename T> int fast_scatter_width(i64 R, i64 Cn) {
   if (!is_pow2(R)) return 0;

@@ -459,6 +459,139 @@ __global__ void __launch_bounds__(W * Sched<LOGN, LOGE>::TPL, 2) fft_slice2d_ker
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Exchange and slice-axis pass of the slab-decomposed 3-D transform in ONE persistent kernel (cube-like shapes, R == S):
+// the CTAs pull work items from an atomic queue whose order interleaves
+//     scatter tiles of column block j+1   (k2 pass of W columns of one local slice, stores to the owners: NVLink)
+//     k1 tiles of column block j          (slice-axis pass of W columns of one received row: local HBM)
+// so that NVLink-bound and HBM-bound tiles share the SMs at a fixed ratio instead of two kernels fighting for slots on
+// two streams.  The last scatter tile of block j on a rank publishes `epoch` into slot (rank, j) of every peer's flag
+// array; a k1 tile of block j polls the P slots (rank h, j) of its own array before it loads.  Scatter tiles never wait,
+// and every scatter tile of blocks <= j+1 has been handed out before the first k1 tile of block j, so the spin-waits
+// cannot dead-lock however the ranks drift; one stream, no second kernel.  Flag layout: slots 0..7 belong to
+// peer_barrier_kernel, slot 8 + 16*rank + block to this kernel (256 int64 per rank).
+template <typename T> struct PipeParams {
+  const cx<T>* a;        // local slab [Ls][R][C] (rows already transformed)
+  cx<T>* peer[8];        // receive buffers [S][Rh][C] of this step, one per rank
+  cx<T>* recv;           // this rank's receive buffer (slice-axis pass in place)
+  long long* flags[8];   // flag arrays of all ranks
+  int* counters;         // [0] work queue, [1 + j] scatter tiles of block j finished on this rank (zeroed before the launch)
+  int* err;
+  const cx<T>* twg;
+  long long epoch;
+  int Ls, C, logRh, P, rank, nb, gpb;   // gpb = W-column groups per block
+  int inverse, has_scale;
+  T scale;
+};
+
+template <typename T, int LOGN, int LOGE, int W>
+__global__ void __launch_bounds__(W * Sched<LOGN, LOGE>::TPL, (Sched<LOGN, LOGE>::E <= 8 ? FastOcc<W * Sched<LOGN, LOGE>::TPL>::MINB
+                                                                                      : (FastOcc<W * Sched<LOGN, LOGE>::TPL>::MINB + 1) / 2))
+fft_pipe_kernel(const PipeParams<T> p) {
+#ifndef JTB_EMU
+  typedef Sched<LOGN, LOGE> S;
+  typedef cx<T> C;
+  typedef FastAddr<T, S, true, W> A;
+  JTB_DYN_SMEM(smem_raw);
+  C* sm = reinterpret_cast<C*>(smem_raw);
+  C* twt = sm + A::TILE;
+  __shared__ int s_item;
+  const int tid = threadIdx.x;
+  const int w = tid % W, t = tid / W;
+  for (int i = tid; i < FastTw<S>::COUNT_SM; i += W * S::TPL) twt[i] = __ldg(p.twg + i);
+  const int Rh = 1 << p.logRh;
+  const int ns = p.Ls * p.gpb;               // tiles per block, both kinds (R == S  =>  Ls * gpb == Rh * gpb)
+  const int total = 2 * p.nb * ns;
+  const int cc = p.gpb * W;
+  // Scatter tiles are counted lazily: a system-scope fence per tile would hold the CTA for an NVLink round trip.  The CTA
+  // remembers how many tiles of block `pend_blk` it has stored and flushes -- every thread fences, one thread adds the
+  // count, the CTA that completes the block publishes it -- when it draws an item beyond that block's scatter range.
+  int pend_blk = -1, pend_cnt = 0;
+  auto flush = [&]() {
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      if (atomicAdd(p.counters + 1 + pend_blk, pend_cnt) + pend_cnt == ns) {
+        __threadfence_system();
+        for (int h = 0; h < p.P; ++h) *((volatile long long*)(p.flags[h] + 8 + p.rank * 16 + pend_blk)) = p.epoch;
+        __threadfence_system();
+      }
+    }
+    pend_cnt = 0;
+  };
+  for (;;) {
+    __syncthreads();                         // previous tile's shared memory is free; s_item has been read
+    if (tid == 0) s_item = atomicAdd(p.counters, 1);
+    __syncthreads();
+    const int item = s_item;
+    if (pend_cnt > 0 && item >= (pend_blk == 0 ? ns : ns + pend_blk * 2 * ns)) flush();
+    if (item >= total) break;
+    // decode: phase 0 = scatter block 0; phases 1..nb-1 = scatter block ph interleaved with k1 block ph-1; phase nb = k1 block nb-1
+    int blk, idx;
+    bool scatter;
+    if (item < ns) { scatter = true; blk = 0; idx = item; }
+    else if (item >= total - ns) { scatter = false; blk = p.nb - 1; idx = item - (total - ns); }
+    else {
+      const int r = item - ns, ph = r / (2 * ns), o = r - ph * 2 * ns;
+      scatter = (o & 1) == 0; idx = o >> 1; blk = scatter ? ph + 1 : ph;
+    }
+    const int i1 = idx / p.gpb, cg = idx - i1 * p.gpb;
+    const int c = blk * cc + cg * W + w;
+    C v[S::E];
+    if (scatter) {
+      const C* src = p.a + (i64)i1 * S::N * p.C + c;
+#pragma unroll
+      for (int q = 0; q < S::E; ++q) v[q] = src[(i64)(t + q * S::TPL) * p.C];
+    } else {
+      if (tid == 0) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (int h = 0; h < p.P; ++h) {
+          volatile long long* f = p.flags[p.rank] + 8 + h * 16 + blk;
+          while (*f < p.epoch) {
+            __nanosleep(200);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 10000000000ULL) { *p.err = 2; break; }
+          }
+        }
+        __threadfence_system();
+      }
+      __syncthreads();
+      const C* src = p.recv + (i64)i1 * p.C + c;          // row i1 of every slice: elements Rh*C apart
+#pragma unroll
+      for (int q = 0; q < S::E; ++q) v[q] = __ldcg(src + (i64)(t + q * S::TPL) * Rh * p.C);
+    }
+    if (p.inverse) {
+#pragma unroll
+      for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
+    }
+    FastLoop<T, S, 0, true, W>::run(v, sm, twt, t, w, p.twg);
+    if (!scatter && p.has_scale) {
+#pragma unroll
+      for (int q = 0; q < S::E; ++q) { v[q].x *= p.scale; v[q].y *= p.scale; }
+    }
+    if (p.inverse) {
+#pragma unroll
+      for (int q = 0; q < S::E; ++q) v[q] = cswap(v[q]);
+    }
+    if (scatter) {
+      const i64 row0 = ((i64)p.rank * p.Ls + i1) * Rh;
+#pragma unroll
+      for (int q = 0; q < S::E; ++q) {
+        const int k2 = t + q * S::TPL;
+        p.peer[k2 >> p.logRh][(row0 + (k2 & (Rh - 1))) * p.C + c] = v[q];
+      }
+      pend_blk = blk;                         // (a CTA never holds tiles of two blocks: the flush above came first)
+      ++pend_cnt;
+    } else {
+      C* dst = p.recv + (i64)i1 * p.C + c;
+#pragma unroll
+      for (int q = 0; q < S::E; ++q) dst[(i64)(t + q * S::TPL) * Rh * p.C] = v[q];
+    }
+  }
+#endif
+}
+
 // cross-GPU barrier: thread h publishes `epoch` into rank h's flag array (slot = my rank) and waits until
 // rank h has published it into mine.  flags are peer-mapped int64[nranks] arrays, monotonically increasing.
 struct PeerFlags { long long* f[8]; };

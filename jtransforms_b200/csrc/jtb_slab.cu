@@ -135,6 +135,8 @@ struct jtb_slab {
   // pipelined exchange (forward, fused peer stores): the slab is sent column block by column block and the slice-axis
   // pass of block j runs on `st2` as soon as block j has arrived from every peer, under the stores of blocks j+1..
   int nchunks = 1;                       // column blocks per step (JTB_SLAB_CHUNKS; 1 = one exchange, then the k1 pass)
+  int fused_blocks = 0;                  // > 0: exchange + slice-axis pass in one persistent kernel (JTB_SLAB_FUSED)
+  int* pipe_counters = nullptr;          // work queue + per-block tile counters of fft_pipe_kernel
   cudaStream_t st2 = nullptr;            // high-priority stream of the consumer side
   cudaEvent_t evc[16];                   // same-process groups: block j of this member has been stored
   cudaEvent_t ev_join = nullptr;
@@ -344,6 +346,24 @@ template <typename T> int slab_pipe_consume(jtb_slab* m, bool inverse, bool scal
   return ST_OK;
 }
 
+// ---- exchange + slice-axis pass in one persistent kernel (fft_pipe_kernel): rows, then ONE launch
+template <typename T> bool slab_fused_ok(const jtb_slab* m) {
+  return m->P > 1 && m->exchange == 0 && m->fused_blocks > 0 && fast_pipe_has<T>(m->R, m->S, m->Cn, m->P, m->fused_blocks);
+}
+template <typename T> int slab_fused_step(jtb_slab* m, cx<T>* a, bool inverse, bool scale, cudaStream_t st, int buf) {
+  Engine<T> e(m->ctx, st);
+  const i64 Ls = m->Ls, R = m->R, Cn = m->Cn;
+  JTB_TRY(e.c2c_lines(a, geo_contig(Cn), Ls * R, Cn, inverse, false, (T)1));
+  JTB_CUDA(cudaMemsetAsync(m->pipe_counters, 0, 32 * sizeof(int), st));
+  const long long epoch = ++m->epoch;
+  bool handled = false;
+  JTB_TRY(fast_pipe_exchange<T>(e, a, Ls, R, Cn, m->P, m->rank, m->peer_recv[buf], (void* const*)m->peer_flags, epoch,
+                                m->pipe_counters, m->fused_blocks, inverse, scale,
+                                (T)(1.0 / ((double)m->S * (double)R * (double)Cn)), &handled));
+  if (!handled) { set_error("internal: fused exchange kernel unavailable"); return ST_UNSUPPORTED; }
+  return ST_OK;
+}
+
 int slab_check_buffers(jtb_slab* m) {
   if (m->P > 1 && (m->mode == 0 || !m->recv[0])) { set_error("slab member is not connected to its peers"); return ST_ARG; }
   return ST_OK;
@@ -389,6 +409,29 @@ int slab_group_run(jtb_slab* const* ms, int n, void* const* a, bool back, bool i
     JTB_TRY(slab_check_buffers(ms[g]));
   }
   const int buf = ms[0]->step & 1;
+  {
+    bool fused = !back && (f64 ? slab_fused_ok<double>(ms[0]) : slab_fused_ok<float>(ms[0]));
+    for (int g = 0; g < n && fused; ++g)          // persistent spinning CTAs: every member needs a GPU of its own
+      for (int h = 0; h < g; ++h)
+        if (ms[g]->device == ms[h]->device) fused = false;
+    if (fused) {
+      for (int g = 0; g < n; ++g) {
+        jtb_slab* m = ms[g];
+        DeviceGuard dg(m->device);
+        JTB_TRY(m->ctx->order_begin(st[g]));
+        JTB_TRY(m->mark(0, st[g]));
+        JTB_TRY(f64 ? slab_fused_step<double>(m, (double2*)a[g], inverse, scale, st[g], buf)
+                    : slab_fused_step<float>(m, (float2*)a[g], inverse, scale, st[g], buf));
+        JTB_TRY(m->mark(1, st[g]));
+        JTB_TRY(m->mark(2, st[g]));
+        JTB_TRY(m->mark(3, st[g]));
+        JTB_TRY(m->ctx->order_end(st[g]));
+        results[g] = m->recv[buf];
+        m->step++;
+      }
+      return ST_OK;
+    }
+  }
   const int nb = back ? 1 : (f64 ? slab_pipe_blocks<double>(ms[0]) : slab_pipe_blocks<float>(ms[0]));
   if (nb > 1) {
     for (int g = 0; g < n; ++g) {
@@ -499,6 +542,8 @@ int jtb_slab_create(jtb_slab** out, int prec, int64_t S, int64_t R, int64_t Cn, 
   {
     static const char* ex = getenv("JTB_EXCHANGE_NCCL");
     m->exchange = (ex && atoi(ex)) ? 1 : 0;
+    static const char* fu = getenv("JTB_SLAB_FUSED");
+    m->fused_blocks = fu ? atoi(fu) : 0;
     static const char* ch = getenv("JTB_SLAB_CHUNKS");
     // Measured on 2 x B200, 512^3 (profiles/r02_pipe_timeline_2gpu.log): the blocks do overlap, but the peer-store
     // exchange needs every SM's store slots -- a block's stores take 0.20 ms alone and 0.31 ms next to the slice-axis
@@ -510,8 +555,9 @@ int jtb_slab_create(jtb_slab** out, int prec, int64_t S, int64_t R, int64_t Cn, 
   if (nranks > 1) {
     cudaError_t e = cudaMalloc(&m->recv[0], m->block_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&m->recv[1], m->block_bytes);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&m->flags, 8 * sizeof(long long));
-    if (e == cudaSuccess) e = cudaMemset(m->flags, 0, 8 * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->flags, 256 * sizeof(long long));   // 8 barrier slots + 8 x 16 block slots
+    if (e == cudaSuccess) e = cudaMemset(m->flags, 0, 256 * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->pipe_counters, 32 * sizeof(int));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev, cudaEventDisableTiming);
     if (e != cudaSuccess) {
       const int rc = cuda_fail(e, "slab buffers");
@@ -539,6 +585,7 @@ int jtb_slab_destroy(jtb_slab* m) {
 #endif
   for (int b = 0; b < 2; ++b) if (m->recv[b]) cudaFree(m->recv[b]);
   if (m->flags) cudaFree(m->flags);
+  if (m->pipe_counters) cudaFree(m->pipe_counters);
   if (m->ev) cudaEventDestroy(m->ev);
   if (m->st2) cudaStreamDestroy(m->st2);
   if (m->ev_join) cudaEventDestroy(m->ev_join);
@@ -702,6 +749,17 @@ static int slab_member_run(jtb_slab* m, void* a, bool back, bool inverse, bool s
   JTB_TRY(slab_check_buffers(m));
   JTB_TRY(m->ctx->order_begin(st));
   const int buf = m->step & 1;
+  if (!back && (f64 ? slab_fused_ok<double>(m) : slab_fused_ok<float>(m))) {
+    JTB_TRY(m->mark(0, st));
+    JTB_TRY(f64 ? slab_fused_step<double>(m, (double2*)a, inverse, scale, st, buf) : slab_fused_step<float>(m, (float2*)a, inverse, scale, st, buf));
+    JTB_TRY(m->mark(1, st));
+    JTB_TRY(m->mark(2, st));
+    JTB_TRY(m->mark(3, st));
+    m->step++;
+    JTB_TRY(m->ctx->order_end(st));
+    *result = m->recv[buf];
+    return ST_OK;
+  }
   {
     const int nb = back ? 1 : (f64 ? slab_pipe_blocks<double>(m) : slab_pipe_blocks<float>(m));
     if (nb > 1) {
