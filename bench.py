@@ -512,10 +512,23 @@ def main():
         else:
             passes += [("k2 columns (stride C, in place)", "fft_fast_kernel<double,9,3,strided,8>", lambda: lines(ap_, R, Cn * S, Cn, 1, R * Cn, Cn)),
                        ("k1 slices (stride R*C, in place)", "fft_fast_kernel<double,9,3,strided,8>", lambda: lines(ap_, S, R * Cn, R * Cn, 1, S * R * Cn, R * Cn))]
+        # timed IN SEQUENCE (k3, k2, k1, k3, ... exactly like consecutive steps) with an event between the launches, so
+        # that every pass sees the cache / TLB / clock state it has inside the step
+        for _, _, fn in passes:
+            fn()
+        fill(a, seed0)
+        reps = max(3, min(args.steps, 10))
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(passes) + 1)] for _ in range(reps)]
+        torch.cuda.synchronize()
+        for r in range(reps):
+            evs[r][0].record()
+            for i, (_, _, fn) in enumerate(passes):
+                fn()
+                evs[r][i + 1].record()
+        torch.cuda.synchronize()
         per = []
-        for name, kern, fn in passes:
-            fill(a, seed0)
-            t_ms = timed(fn)
+        for i, (name, kern, _) in enumerate(passes):
+            t_ms = sum(evs[r][i].elapsed_time(evs[r][i + 1]) for r in range(reps)) / reps
             per.append({"pass": name, "kernel": kern, "ms": t_ms, "GBps": 2 * local_bytes / (t_ms * 1e-3) / 1e9,
                         "frac": 2 * local_bytes / (t_ms * 1e-3) / 1e9 / hbm_peak})
         del wk
