@@ -466,3 +466,14 @@ def test_fft1d_mixed_two_pass_batch_and_real(jt):
     for b in range(3):
         assert o.rel_l2(a[2 * n * b:2 * n * (b + 1)], o.complex_forward_1d(x[2 * n * b:2 * n * (b + 1)], n)) < 1e-12 * 14
     pc.fft1d_real(jt, "Double", 12000)
+
+
+@pytest.mark.parametrize("chunks", ["2", "4"])
+def test_multi_device_plan_pipelined_exchange(jt, chunks):
+    """the opt-in column-block pipelined exchange (JTB_SLAB_CHUNKS: windowed scatter launches, per-block events,
+    slice-axis pass per block on the second stream) gives the same result as the default step"""
+    import sys
+    env = dict(os.environ, JTB_SLAB_CHUNKS=chunks)
+    r = subprocess.run([sys.executable, os.path.join(HERE, "helpers", "pipe_group_emu.py"), EMU_LIB], env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
