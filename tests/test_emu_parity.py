@@ -477,3 +477,17 @@ def test_multi_device_plan_pipelined_exchange(jt, chunks):
     r = subprocess.run([sys.executable, os.path.join(HERE, "helpers", "pipe_group_emu.py"), EMU_LIB], env=env,
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("prec", ["Double", "Float"])
+@pytest.mark.parametrize("dims", [(64, 128), (2, 64), (128, 1024), (16, 8192)])
+def test_dht2d_rows_with_folded_ytransform(jt, prec, dims):
+    """DoubleDHT_2D: the row pass owns the row pairs (r, R-r) and applies yTransform (dht/DoubleDHT_2D.java:1288-1309) in
+    its store (fast_dht2d_rows) -- forward, scaled and unscaled inverse against the oracle"""
+    pc.r2r(jt, prec, "DHT", dims)
+    from jtransforms_b200 import _lib
+    lib = _lib.get()
+    x = pc.rnd(dims[0] * dims[1]).astype(pc.dtype_of(prec))
+    l0 = lib.jtb_launch_count(0)
+    getattr(jt, prec + "DHT_2D")(*dims).forward(x)
+    assert lib.jtb_launch_count(0) - l0 <= (2 if dims[0] >= 32 else 4)      # no separate yTransform launch
