@@ -41,6 +41,25 @@ def classes():
     yield "fft", "RealFFTUtils_3D"
 
 
+def test_common_utils_user_surface():
+    """utils/CommonUtils: the user-facing statics (thresholds, power-of-two helpers, getReminder: reference lines 67-332)
+    exist with the same signatures; the Ooura routines below them are the hot path itself and are not mirrored"""
+    mine = signatures(os.path.join(ROOT, "java", "org", "jtransforms", "utils", "CommonUtils.java"))
+    if not os.path.isdir(REF):
+        pytest.skip("reference checkout not present")
+    src = open(os.path.join(REF, "utils", "CommonUtils.java")).read().split("public static void makeipt")[0]
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    ref = set()
+    for m in re.finditer(r"public\s+static\s+(?:void|int|long|boolean)\s+(\w+)\s*\(([^)]*)\)", src):
+        types = tuple(re.sub(r"\bfinal\s+", "", a.strip()).rsplit(None, 1)[0].replace(" ", "") for a in m.group(2).split(",") if a.strip())
+        ref.add((m.group(1), types))
+    got = set()
+    for m in re.finditer(r"public\s+static\s+(?:void|int|long|boolean)\s+(\w+)\s*\(([^)]*)\)", open(os.path.join(ROOT, "java", "org", "jtransforms", "utils", "CommonUtils.java")).read()):
+        types = tuple(a.strip().rsplit(None, 1)[0].replace(" ", "") for a in m.group(2).split(",") if a.strip())
+        got.add((m.group(1), types))
+    assert not sorted(ref - got), sorted(ref - got)
+
+
 def test_generator_is_up_to_date(tmp_path):
     before = {}
     for pkg, cls in classes():
