@@ -491,3 +491,18 @@ def test_dht2d_rows_with_folded_ytransform(jt, prec, dims):
     l0 = lib.jtb_launch_count(0)
     getattr(jt, prec + "DHT_2D")(*dims).forward(x)
     assert lib.jtb_launch_count(0) - l0 <= (2 if dims[0] >= 32 else 4)      # no separate yTransform launch
+
+
+@pytest.mark.parametrize("prec", ["Float", "Double"])
+def test_batch_split_over_plan_devices(jt, prec):
+    """jtb_exec_batch on a multi-GPU plan: contiguous blocks of the batch per listed device (ragged: 7 lines over 3
+    members), one host thread and one pipeline each -- BASELINE config 3's sharding behind the drop-in call"""
+    n, howmany = 1009, 7
+    dt = pc.dtype_of(prec)
+    x = pc.rnd(2 * n * howmany).astype(dt)
+    a = x.copy()
+    f = getattr(jt, prec + "FFT_1D")(n, devices=[0, 0, 0])
+    f.complexForwardBatch(a, howmany, 2 * n)
+    for b in range(howmany):
+        want = o.complex_forward_1d(x[2 * n * b:2 * n * (b + 1)].astype(np.float64), n)
+        pc.check(a[2 * n * b:2 * n * (b + 1)], want, prec, n, "batch line %d" % b)
